@@ -1,0 +1,323 @@
+#!/usr/bin/env python
+"""Benchmark of the DRR hot path: DRRs/sec (trilinear forward + backward w.r.t. the pose), 512^3 CT, 256x256
+detector, batch of 116 poses per GPU (BASELINE.json configs[1]), with the kernel's HBM roofline and the
+reference's CPU path (the oracle restatement on real grid_sample) timed on the same box.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+N > 1 is launched by torchrun (one rank per GPU, NCCL); poses shard across ranks with no data-path collective
+(weak scaling: every rank renders its own 116 poses of a replicated volume).
+"""
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+VOL_N = 512
+DET = 256
+BATCH = 116
+N_POINTS = 500
+SDD = 1020.0
+DELX = 1.08821875
+POSE_RANGES = dict(alphamin=-45, alphamax=45, betamin=-45, betamax=45, gammamin=-15, gammamax=15, txmin=-50,
+                   txmax=50, tymin=700, tymax=900, tzmin=-50, tzmax=50)
+METRIC = "DRRs/sec (fwd+bwd) 512^3 vol @256^2 det"
+UNIT = "DRR/s"
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def algorithmic_bytes_fwd(h, w, n_points):
+    """SURVEY.md 8(d) gather model: 8 corner voxels x 4 B per sample + the output pixel."""
+    return h * w * (n_points * 32 + 4)
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons, power = [], [], set(), []
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "reasons": sorted(reasons),
+                "power_w_max": max(power), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ scene
+def pose_batch(batch, seed):
+    from xvr_b200.sampler import random_pose_params
+
+    g = torch.Generator().manual_seed(seed)
+    rot, xyz = random_pose_params(**POSE_RANGES, batch_size=batch, generator=g)
+    return torch.deg2rad(rot), xyz
+
+
+def build_scene(device, vol_n=VOL_N, det=DET):
+    import xvr_b200
+    from xvr_b200.data import read, synthetic_ct
+
+    hu, _, affine = synthetic_ct(vol_n, seed=0, device=device)
+    sub = read(hu, affine=affine)
+    del hu
+    drr = xvr_b200.DRR(sub, SDD, det, DELX * 256.0 / det, renderer="trilinear", reverse_x_axis=False).to(device)
+    return drr
+
+
+# ------------------------------------------------------------------------------------------ CPU reference arm
+def cpu_reference_step(density, affinv, reorient, rot, xyz, rows, det, gout):
+    """One fwd+bwd(pose) of the oracle (DiffDRR glue on real grid_sample) over a subset of detector rows."""
+    import oracle
+
+    rot = rot.clone().requires_grad_()
+    xyz = xyz.clone().requires_grad_()
+    pose = oracle.pose_from_params(rot, xyz, "euler_angles", "ZXY")
+    src, tgt = oracle.detector_rays(pose, reorient, det, det, DELX * 256.0 / det, DELX * 256.0 / det, 0.0, 0.0, SDD, False)
+    tgt = tgt.view(len(rot), det, det, 3)[:, rows].reshape(len(rot), -1, 3)
+    raylen = (tgt - src).norm(dim=-1).unsqueeze(1)
+    src, tgt = oracle.apply(affinv, src), oracle.apply(affinv, tgt)
+    img = oracle.trilinear_render(density, src, tgt, raylen, n_points=N_POINTS)
+    (img * gout).sum().backward()
+    return img.detach(), rot.grad, xyz.grad
+
+
+def cpu_reference(steps, warmup, vol_n=VOL_N, det=DET, target_seconds=8.0):
+    """Time the reference's CPU path on this box's host cores on a bounded sample of the workload."""
+    import numpy as np
+
+    from xvr_b200.data import REORIENT, read, synthetic_ct
+
+    threads = torch.get_num_threads()
+    hu, _, affine = synthetic_ct(vol_n, seed=0)
+    sub = read(hu, affine=affine)
+    density = sub.density
+    affinv = torch.as_tensor(np.linalg.inv(sub.volume.affine), dtype=torch.float32)[None]
+    reorient = torch.tensor(REORIENT["AP"])
+    # ATen's CPU grid_sampler_3d parallelises over the batch dimension only -> one pose per thread
+    b = max(4, min(threads, 32, BATCH))
+    rot, xyz = pose_batch(BATCH, seed=0)
+    rot, xyz = rot[:b], xyz[:b]
+    n_rows = max(1, det // 32)
+    rows = torch.arange(0, det, det // n_rows)[:n_rows]
+    gout = torch.rand(b, 1, len(rows) * det, generator=torch.Generator().manual_seed(1))
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        cpu_reference_step(density, affinv, reorient, rot, xyz, rows, det, gout)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    drr_equiv = b * len(rows) / det
+    t = sum(times)
+    sample = (f"{b} poses x {len(rows)} of {det} detector rows ({len(rows) * det} rays each, {N_POINTS} samples/ray) "
+              f"of the {vol_n}^3 volume per step = {drr_equiv:.3f} DRR-equivalents; fwd+bwd(pose) through autograd")
+    return {"value": drr_equiv * len(times) / t, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+            "seconds_per_step": t / len(times)}
+
+
+# ------------------------------------------------------------------------------------------ main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--vol", type=int, default=VOL_N)
+    ap.add_argument("--det", type=int, default=DET)
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    workload = (f"{args.vol}^3 synthetic CT (fp32), batch={args.batch} poses per GPU, {args.det}x{args.det} detector, "
+                f"trilinear n_points={N_POINTS}, fwd + bwd w.r.t. 6-DoF pose")
+    config = {"workload": workload, "renderer": "trilinear", "parallelism": f"pose-sharded x{world}",
+              "l2_policy": f"volume ({args.vol ** 3 * 4 / 2 ** 20:.0f} MiB) exceeds the 126 MB L2; no flush"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        steps, warmup = max(1, min(args.steps, 3)), min(args.warmup, 1)
+        res = cpu_reference(steps, warmup, args.vol, args.det)
+        line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
+                "steps": steps, "warmup": warmup, "ms_per_step": res["seconds_per_step"] * 1e3,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": config, "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=device)
+
+    import xvr_b200
+    from xvr_b200 import _lib
+
+    drr = build_scene(device, args.vol, args.det)
+    B, H, W = args.batch, args.det, args.det
+    rot_h, xyz_h = pose_batch(B, seed=rank)
+    rot_h, xyz_h = rot_h.pin_memory(), xyz_h.pin_memory()
+    gout = torch.rand(B, 1, H, W, device=device, generator=torch.Generator(device=device).manual_seed(1))
+    img_h = torch.empty(B, 1, H, W, pin_memory=True)
+    grad_h = torch.empty(B, 6, pin_memory=True)
+
+    def step(rot, xyz):
+        rot = rot.detach().requires_grad_()
+        xyz = xyz.detach().requires_grad_()
+        pose = xvr_b200.convert(rot, xyz, parameterization="euler_angles", convention="ZXY")
+        img = drr(pose)
+        img.backward(gout)
+        return img, rot.grad, xyz.grad
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    rot_d, xyz_d = rot_h.to(device), xyz_h.to(device)
+    for _ in range(max(args.warmup, 3)):
+        step(rot_d, xyz_d)
+    barrier()
+
+    # ---- device-resident timing ("value")
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    _lib.start_profile()
+    launches0 = _lib.lib().xvr_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step(rot_d, xyz_d)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = _lib.lib().xvr_launch_count() - launches0
+    kernel_ms = _lib.stop_profile()
+
+    # ---- end-to-end timing through the public API with host buffers ("e2e")
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for _ in range(args.steps):
+        r, x = rot_h.to(device, non_blocking=True), xyz_h.to(device, non_blocking=True)
+        img, gr, gx = step(r, x)
+        img_h.copy_(img, non_blocking=True)
+        grad_h[:, :3].copy_(gr, non_blocking=True)
+        grad_h[:, 3:].copy_(gx, non_blocking=True)
+        torch.cuda.current_stream().synchronize()  # the caller reads the result every step
+    e3.record()
+    barrier()
+    ms_e2e = e2.elapsed_time(e3)
+    clocks = sampler.stop() if rank == 0 else None
+
+    t = torch.tensor([ms, ms_e2e], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = t.tolist()
+
+    if rank == 0:
+        total = world * B * args.steps
+        value = total / (ms * 1e-3)
+        peak, peak_src = peaks()
+        name = "xvr_trilinear_rays_fwd"
+        k_ms = kernel_ms.get(name, [])
+        k_avg = sum(k_ms) / len(k_ms) if k_ms else float("nan")
+        alg = B * algorithmic_bytes_fwd(H, W, N_POINTS)
+        achieved = alg / (k_avg * 1e-3) / 1e9
+        step_share = {k: sum(v) / ms for k, v in kernel_ms.items()}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+            "e2e": {"value": total / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": B * 6 * 4,
+                    "d2h_bytes_per_step": B * H * W * 4 + B * 6 * 4},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "trilinear_fwd_kernel<JAC=true> (one gather pass yields the DRR "
+                         "and its per-ray pose Jacobian; the backward is a 28 B/ray epilogue)",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg,
+                         "kernel_ms": k_avg},
+            "roofline_step": {"note": "SURVEY 8(d) fwd+bwd(pose) figure (two gather passes, 2.0977 GB/DRR) over the "
+                              "whole step time", "achieved": 2 * alg * args.steps / (ms * 1e-3) / 1e9 / 1.0,
+                              "frac": 2 * alg * args.steps / (ms * 1e-3) / 1e9 / peak},
+            "kernel_share_of_step": step_share,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            res = cpu_reference(1, 1, args.vol, args.det)
+            line["cpu_baseline"] = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,104 @@
+"""ctypes binding of libxvr_b200.so -- the C-ABI declared in include/xvr_b200.h.
+
+There is no CPU or PyTorch fallback: if the shared library is missing or a call fails, an exception is
+raised.  Tensors cross the boundary as raw device pointers + sizes; the CUDA stream is torch's current one.
+"""
+
+import ctypes
+from ctypes import c_float, c_int, c_int64, c_void_p
+
+import torch
+
+from ._build import LIB
+
+_lib = None
+
+P = c_void_p
+_SIGNATURES = {
+    "xvr_abi_version": ([], c_int),
+    "xvr_last_error": ([], ctypes.c_char_p),
+    "xvr_launch_count": ([], c_int64),
+    "xvr_trilinear_rays_fwd": (
+        [P, c_int, c_int, c_int, P, c_int, P, P, P, c_int, c_int, c_int, c_int, c_float, c_int, c_int, c_int,
+         c_int, P, P, P], c_int),
+    "xvr_trilinear_rays_bwd": (
+        [P, c_int, c_int, c_int, P, c_int, P, P, P, c_int, c_int, c_int, c_int, c_float, c_int, c_int, c_int,
+         c_int, P, P, P, P, P, P], c_int),
+    "xvr_rays_jac_bwd": ([P, P, c_int, c_int, P, P, P, P, P], c_int),
+}
+
+
+class XvrB200Error(RuntimeError):
+    pass
+
+
+def lib():
+    """Load the library once; fail loudly if it has not been built (python -m xvr_b200._build)."""
+    global _lib
+    if _lib is None:
+        if not LIB.exists():
+            raise XvrB200Error(
+                f"{LIB} is missing: build it with `python -m xvr_b200._build` (needs nvcc). "
+                "xvr_b200 has no CPU/PyTorch fallback."
+            )
+        _lib = ctypes.CDLL(str(LIB))
+        for name, (argtypes, restype) in _SIGNATURES.items():
+            fn = getattr(_lib, name)
+            fn.argtypes = argtypes
+            fn.restype = restype
+    return _lib
+
+
+def exported_symbols():
+    return list(_SIGNATURES)
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    return None if t is None else c_void_p(t.data_ptr())
+
+
+def stream():
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def check(rc, name):
+    if rc != 0:
+        raise XvrB200Error(f"{name} failed (code {rc}): {lib().xvr_last_error().decode()}")
+
+
+_profile = None
+
+
+def start_profile():
+    """Record a CUDA-event pair around every C-ABI call (on torch's current stream) until stop_profile()."""
+    global _profile
+    _profile = {}
+
+
+def stop_profile():
+    """-> {entry point: [ms per call]}"""
+    global _profile
+    prof, _profile = _profile, None
+    torch.cuda.synchronize()
+    return {k: [a.elapsed_time(b) for a, b in v] for k, v in (prof or {}).items()}
+
+
+def call(name, *args):
+    if _profile is None:
+        check(getattr(lib(), name)(*args), name)
+        return
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    check(getattr(lib(), name)(*args), name)
+    b.record()
+    _profile.setdefault(name, []).append((a, b))
+
+
+def cuda_f32(t, what):
+    """The kernels take contiguous fp32 CUDA tensors; anything else is an error, not a silent fallback."""
+    if not t.is_cuda:
+        raise XvrB200Error(f"{what} must be a CUDA tensor (xvr_b200 has no CPU path); got {t.device}")
+    if t.dtype != torch.float32:
+        t = t.to(torch.float32)
+    return t.contiguous()

@@ -1,0 +1,164 @@
+// Shared device helpers for the xvr_b200 DRR hot path (sm_100a).
+//
+// Coordinates: the CT volume is a dense fp32 array vol[D0][D1][D2] (D2 contiguous). Ray end points are
+// given in voxel-index coordinates (what xvr obtains from drr.affine_inverse at
+// /root/reference/src/xvr/model/trainer.py:285), so component a of a point indexes volume axis a.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define XVR_OK 0
+#define XVR_ERR_INVALID -1
+#define XVR_ERR_CUDA -2
+
+namespace xvr {
+
+void set_last_error(const char* msg);
+int check_launch(const char* what);
+
+struct Vol {
+  const float* __restrict__ data;
+  int D0, D1, D2;
+  int s0, s1;  // element strides of axis 0 / 1 (D1*D2, D2)
+};
+
+// Slab test of the segment s + alpha*d, alpha in [0,1], against the box [lo, hi]^3 (per axis).
+// Restates DiffDRR renderers._get_alpha_minmax: per-axis (plane - s)/d with IEEE division, min/max over the
+// two planes, max/min over axes, then the clamp to [0,1].  Also reports which plane is active for the
+// analytic pose gradient (axis index, plane coordinate; axis = -1 when the clamp is active).
+struct AlphaRange {
+  float amin, amax;
+  int axis_min, axis_max;      // active axis, or -1 if clamped
+  float plane_min, plane_max;  // plane coordinate of the active crossing
+};
+
+__device__ __forceinline__ AlphaRange alpha_range(const float s[3], const float d[3], const float lo[3],
+                                                  const float hi[3]) {
+  AlphaRange r;
+  r.amin = -INFINITY;
+  r.amax = INFINITY;
+  r.axis_min = -1;
+  r.axis_max = -1;
+  r.plane_min = 0.f;
+  r.plane_max = 0.f;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    float a0 = __fdiv_rn(lo[a] - s[a], d[a]);
+    float a1 = __fdiv_rn(hi[a] - s[a], d[a]);
+    float mn, mx, pmn, pmx;
+    if (a0 <= a1) { mn = a0; mx = a1; pmn = lo[a]; pmx = hi[a]; }
+    else          { mn = a1; mx = a0; pmn = hi[a]; pmx = lo[a]; }
+    if (mn > r.amin) { r.amin = mn; r.axis_min = a; r.plane_min = pmn; }
+    if (mx < r.amax) { r.amax = mx; r.axis_max = a; r.plane_max = pmx; }
+  }
+  if (r.amin < 0.f) { r.amin = 0.f; r.axis_min = -1; }
+  if (r.amax > 1.f) { r.amax = 1.f; r.axis_max = -1; }
+  return r;
+}
+
+// torch.linspace(0, 1, n)[k] in fp32 (ATen RangeFactories: symmetric evaluation around the midpoint).
+__device__ __forceinline__ float linspace01(int k, int n, float step) {
+  return (k < n / 2) ? step * (float)k : 1.0f - step * (float)(n - 1 - k);
+}
+
+// One trilinear sample with zero padding (grid_sample mode="bilinear", padding_mode="zeros",
+// align_corners=True on a grid normalised with dims = shape-1, i.e. the sampler coordinate IS the voxel index;
+// ATen/native/cuda/GridSampler.cuh:23-31 and the out-of-bounds handling at :225-227).
+// GRAD additionally returns the spatial gradient dV/dx (zero-padded corners differentiate as zeros,
+// which is what grid_sampler_3d_backward computes).
+template <bool GRAD>
+__device__ __forceinline__ float sample_trilinear(const Vol& v, float x, float y, float z, float g[3]) {
+  float fx0 = floorf(x), fy0 = floorf(y), fz0 = floorf(z);
+  int ix = (int)fx0, iy = (int)fy0, iz = (int)fz0;
+  float fx = x - fx0, fy = y - fy0, fz = z - fz0;
+  float c000, c001, c010, c011, c100, c101, c110, c111;
+  if ((unsigned)ix < (unsigned)(v.D0 - 1) && (unsigned)iy < (unsigned)(v.D1 - 1) &&
+      (unsigned)iz < (unsigned)(v.D2 - 1)) {
+    const float* p = v.data + ((int64_t)ix * v.s0 + iy * v.s1 + iz);
+    c000 = __ldg(p);
+    c001 = __ldg(p + 1);
+    c010 = __ldg(p + v.s1);
+    c011 = __ldg(p + v.s1 + 1);
+    c100 = __ldg(p + v.s0);
+    c101 = __ldg(p + v.s0 + 1);
+    c110 = __ldg(p + v.s0 + v.s1);
+    c111 = __ldg(p + v.s0 + v.s1 + 1);
+  } else {
+    // Border / outside: fetch each corner only if it is inside the volume, else 0.
+    // Coordinates far outside (|x| huge, NaN) fall through with every corner rejected.
+    if (!(x > -1.f && x < (float)v.D0 && y > -1.f && y < (float)v.D1 && z > -1.f && z < (float)v.D2)) {
+      if (GRAD) { g[0] = g[1] = g[2] = 0.f; }
+      return 0.f;
+    }
+    bool x0 = ix >= 0, x1 = ix + 1 < v.D0;
+    bool y0 = iy >= 0, y1 = iy + 1 < v.D1;
+    bool z0 = iz >= 0, z1 = iz + 1 < v.D2;
+    const float* p = v.data + ((int64_t)ix * v.s0 + iy * v.s1 + iz);
+    c000 = (x0 && y0 && z0) ? __ldg(p) : 0.f;
+    c001 = (x0 && y0 && z1) ? __ldg(p + 1) : 0.f;
+    c010 = (x0 && y1 && z0) ? __ldg(p + v.s1) : 0.f;
+    c011 = (x0 && y1 && z1) ? __ldg(p + v.s1 + 1) : 0.f;
+    c100 = (x1 && y0 && z0) ? __ldg(p + v.s0) : 0.f;
+    c101 = (x1 && y0 && z1) ? __ldg(p + v.s0 + 1) : 0.f;
+    c110 = (x1 && y1 && z0) ? __ldg(p + v.s0 + v.s1) : 0.f;
+    c111 = (x1 && y1 && z1) ? __ldg(p + v.s0 + v.s1 + 1) : 0.f;
+  }
+  // interpolate along z (contiguous), then y, then x
+  float dz00 = c001 - c000, dz01 = c011 - c010, dz10 = c101 - c100, dz11 = c111 - c110;
+  float c00 = fmaf(fz, dz00, c000), c01 = fmaf(fz, dz01, c010);
+  float c10 = fmaf(fz, dz10, c100), c11 = fmaf(fz, dz11, c110);
+  float dy0 = c01 - c00, dy1 = c11 - c10;
+  float c0 = fmaf(fy, dy0, c00), c1 = fmaf(fy, dy1, c10);
+  float dx = c1 - c0;
+  if (GRAD) {
+    g[0] = dx;
+    g[1] = fmaf(fx, dy1 - dy0, dy0);
+    float gz0 = fmaf(fy, dz01 - dz00, dz00), gz1 = fmaf(fy, dz11 - dz10, dz10);
+    g[2] = fmaf(fx, gz1 - gz0, gz0);
+  }
+  return fmaf(fx, dx, c0);
+}
+
+// Nearest label lookup at the same sampler coordinate (grid_sample mode="nearest", align_corners=True,
+// zero padding -> channel 0 when outside; GridSampler.cuh nearest branch uses nearbyint = ties-to-even).
+__device__ __forceinline__ int sample_label(const uint8_t* __restrict__ lab, const Vol& v, float x, float y,
+                                            float z) {
+  float rx = nearbyintf(x), ry = nearbyintf(y), rz = nearbyintf(z);
+  if (!(rx >= 0.f && rx < (float)v.D0 && ry >= 0.f && ry < (float)v.D1 && rz >= 0.f && rz < (float)v.D2))
+    return 0;
+  return (int)__ldg(lab + ((int64_t)(int)rx * v.s0 + (int)ry * v.s1 + (int)rz));
+}
+
+// Thread -> detector pixel mapping.  A CTA of 256 threads covers a (256>>cta_w_log2) x (1<<cta_w_log2) pixel
+// tile; inside it each warp covers a (32>>lane_w_log2) x (1<<lane_w_log2) sub-tile, so that the 32 lanes of a
+// gather touch as few 128-byte lines of the volume as the view geometry allows.
+struct TileMap {
+  int W, H;         // detector width/height used for the mapping (N = H*W); W == 0 -> linear ray index
+  int lane_w_log2;  // log2 of the warp sub-tile width
+  int cta_w_log2;   // log2 of the CTA tile width
+  int tiles_x, tiles_y;
+};
+
+__device__ __forceinline__ int tile_ray_index(const TileMap& m, int tile, int tid, int N) {
+  if (m.W == 0) {
+    int n = tile * 256 + tid;
+    return n < N ? n : -1;
+  }
+  int lane = tid & 31, warp = tid >> 5;
+  int lw = m.lane_w_log2, cw = m.cta_w_log2;
+  int lane_j = lane & ((1 << lw) - 1), lane_i = lane >> lw;
+  int wpr_log2 = cw - lw;  // warps per tile row
+  int warp_j = warp & ((1 << wpr_log2) - 1), warp_i = warp >> wpr_log2;
+  int ty = tile / m.tiles_x, tx = tile - ty * m.tiles_x;
+  int j = (tx << cw) + (warp_j << lw) + lane_j;
+  int i = ty * (256 >> cw) + warp_i * (32 >> lw) + lane_i;
+  return (i < m.H && j < m.W) ? i * m.W + j : -1;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+}  // namespace xvr

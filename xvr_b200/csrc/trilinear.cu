@@ -1,0 +1,437 @@
+// Trilinear DRR renderer: forward (+ per-ray analytic Jacobian) and recompute backward.
+//
+// Replaces DiffDRR 0.6.0 renderers.Trilinear.forward and the autograd backward of the grid_sample it is
+// built on, as called from /root/reference/src/xvr/model/trainer.py:288 (drr.renderer(vol, source, target,
+// raylen, mask=seg)) and, through DRR.forward / Registration.forward, from
+// /root/reference/src/xvr/registrar/base.py:249.  One thread owns one ray and marches its n_points samples
+// in registers; nothing of size (B, N, n_points) is ever materialised.
+#include "common.cuh"
+
+namespace xvr {
+
+struct TrilinearParams {
+  Vol vol;
+  const uint8_t* __restrict__ labels;  // nullable, same shape as vol
+  int C;                               // output channels (1 without labels)
+  const float* __restrict__ source;    // (B,1,3) voxel coords
+  const float* __restrict__ target;    // (B,N,3)
+  const float* __restrict__ raylen;    // (B,N) world-mm ray length (trainer.py:284)
+  int B, N;
+  int n_points;
+  int step_mode;  // 0: span/(n-1)   1: span/n   2: 1/n
+  float eps;
+  TileMap map;
+  int tiles_per_pose;
+  float* __restrict__ out;  // (B,C,N)
+  float* __restrict__ jac;  // (B,7,N): dI/ds(3), dI/dt(3), dI/draylen; nullable
+  // backward only
+  const float* __restrict__ gout;  // (B,C,N)
+  float* __restrict__ gtarget;     // (B,N,3)
+  float* __restrict__ gsrc_ray;    // (B,3,N) per-ray source gradient (reduced by reduce_rows)
+  float* __restrict__ graylen;     // (B,N)
+};
+
+__device__ __forceinline__ float step_weight(int mode, float span, int n) {
+  if (mode == 0) return __fdiv_rn(span, (float)(n - 1));
+  if (mode == 1) return __fdiv_rn(span, (float)n);
+  return __fdiv_rn(1.0f, (float)n);
+}
+
+// d(step weight)/d(span)
+__device__ __forceinline__ float step_weight_dspan(int mode, int n) {
+  if (mode == 0) return 1.0f / (float)(n - 1);
+  if (mode == 1) return 1.0f / (float)n;
+  return 0.f;
+}
+
+// Rays whose segment never comes within one voxel of the volume sample only zero padding: the result is an
+// exact 0 and the march can be skipped.
+__device__ __forceinline__ bool misses_padded_box(const float s[3], const float d[3], const Vol& v) {
+  float lo[3] = {-1.f, -1.f, -1.f};
+  float hi[3] = {(float)v.D0, (float)v.D1, (float)v.D2};
+  AlphaRange r = alpha_range(s, d, lo, hi);
+  return !(r.amin < r.amax);
+}
+
+template <bool JAC, bool LABELS>
+__global__ void __launch_bounds__(256) trilinear_fwd_kernel(const TrilinearParams p) {
+  extern __shared__ float chan_acc[];  // LABELS: [C][256]
+  const int b = blockIdx.x / p.tiles_per_pose;
+  const int tile = blockIdx.x - b * p.tiles_per_pose;
+  const int tid = threadIdx.x;
+  const int n = tile_ray_index(p.map, tile, tid, p.N);
+  if (LABELS) {
+    for (int c = 0; c < p.C; ++c) chan_acc[c * 256 + tid] = 0.f;
+  }
+  if (n < 0) return;
+  const int64_t ray = (int64_t)b * p.N + n;
+
+  float s[3], d[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    s[a] = __ldg(p.source + b * 3 + a);
+    d[a] = (__ldg(p.target + ray * 3 + a) - s[a]) + p.eps;
+  }
+  const float L = __ldg(p.raylen + ray);
+  const int np = p.n_points;
+
+  float lo[3] = {0.f, 0.f, 0.f};
+  float hi[3] = {(float)(p.vol.D0 - 1), (float)(p.vol.D1 - 1), (float)(p.vol.D2 - 1)};
+  const AlphaRange ar = alpha_range(s, d, lo, hi);
+  const float span = ar.amax - ar.amin;
+  const float w = step_weight(p.step_mode, span, np);
+
+  float sumV = 0.f;
+  float A[3] = {0.f, 0.f, 0.f}, Bv[3] = {0.f, 0.f, 0.f}, T = 0.f, Q = 0.f;
+
+  if (!misses_padded_box(s, d, p.vol)) {
+    const float lstep = 1.0f / (float)(np - 1);
+#pragma unroll 4
+    for (int k = 0; k < np; ++k) {
+      const float u = linspace01(k, np, lstep);
+      const float alpha = fmaf(u, span, ar.amin);
+      const float x = fmaf(alpha, d[0], s[0]);
+      const float y = fmaf(alpha, d[1], s[1]);
+      const float z = fmaf(alpha, d[2], s[2]);
+      float g[3];
+      const float v = sample_trilinear<JAC>(p.vol, x, y, z, g);
+      if (LABELS) {
+        const int c = sample_label(p.labels, p.vol, x, y, z);
+        chan_acc[c * 256 + tid] += v;
+      } else {
+        sumV += v;
+      }
+      if (JAC) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          A[a] += g[a];
+          Bv[a] = fmaf(alpha, g[a], Bv[a]);
+        }
+        const float gd = fmaf(g[0], d[0], fmaf(g[1], d[1], g[2] * d[2]));
+        T += gd;
+        Q = fmaf(u, gd, Q);
+      }
+    }
+  }
+
+  if (LABELS) {
+    for (int c = 0; c < p.C; ++c) {
+      const float sv = chan_acc[c * 256 + tid];
+      p.out[((int64_t)b * p.C + c) * p.N + n] = sv * L * w;
+      sumV += sv;
+    }
+  } else {
+    p.out[ray] = sumV * L * w;
+  }
+
+  if (JAC) {
+    // I = L * w(span) * sumV,  x_k = s + alpha_k d,  alpha_k = amin + u_k span,  d = t - s + eps.
+    // dI/ds = L [ sumV w' (dspan/ds) + w (A - Bv + P damin/ds + Q damax/ds) ],  P = T - Q
+    // dI/dt = L [ sumV w' (dspan/dt) + w (     Bv + P damin/dt + Q damax/dt) ]
+    // a crossing alpha = (plane - s_a)/d_a has dalpha/ds_a = (alpha-1)/d_a, dalpha/dt_a = -alpha/d_a.
+    const float P = T - Q;
+    const float wp = step_weight_dspan(p.step_mode, np);
+    float js[3], jt[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      js[a] = w * (A[a] - Bv[a]);
+      jt[a] = w * Bv[a];
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      if (ar.axis_min == a) {
+        const float dads = (ar.amin - 1.f) / d[a], dadt = -ar.amin / d[a];
+        js[a] += (w * P - sumV * wp) * dads;
+        jt[a] += (w * P - sumV * wp) * dadt;
+      }
+      if (ar.axis_max == a) {
+        const float dads = (ar.amax - 1.f) / d[a], dadt = -ar.amax / d[a];
+        js[a] += (w * Q + sumV * wp) * dads;
+        jt[a] += (w * Q + sumV * wp) * dadt;
+      }
+    }
+    float* j = p.jac + (int64_t)b * 7 * p.N + n;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      j[(int64_t)a * p.N] = L * js[a];
+      j[(int64_t)(3 + a) * p.N] = L * jt[a];
+    }
+    j[(int64_t)6 * p.N] = sumV * w;
+  }
+}
+
+// Recompute backward: given dL/dout (B,C,N) re-march every ray and emit dL/dtarget (B,N,3), the per-ray
+// dL/dsource (B,3,N) and dL/draylen (B,N).  Handles label channels (the upstream gradient of a sample is the
+// one of the channel its label selects).
+template <bool LABELS>
+__global__ void __launch_bounds__(256) trilinear_bwd_kernel(const TrilinearParams p) {
+  extern __shared__ float chan_g[];  // LABELS: [C][256] upstream gradient per channel
+  const int b = blockIdx.x / p.tiles_per_pose;
+  const int tile = blockIdx.x - b * p.tiles_per_pose;
+  const int tid = threadIdx.x;
+  const int n = tile_ray_index(p.map, tile, tid, p.N);
+  if (n < 0) return;
+  const int64_t ray = (int64_t)b * p.N + n;
+
+  float s[3], d[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    s[a] = __ldg(p.source + b * 3 + a);
+    d[a] = (__ldg(p.target + ray * 3 + a) - s[a]) + p.eps;
+  }
+  const float L = __ldg(p.raylen + ray);
+  const int np = p.n_points;
+  float g1 = 0.f;
+  if (LABELS) {
+    for (int c = 0; c < p.C; ++c) chan_g[c * 256 + tid] = __ldg(p.gout + ((int64_t)b * p.C + c) * p.N + n);
+  } else {
+    g1 = __ldg(p.gout + ray);
+  }
+
+  float lo[3] = {0.f, 0.f, 0.f};
+  float hi[3] = {(float)(p.vol.D0 - 1), (float)(p.vol.D1 - 1), (float)(p.vol.D2 - 1)};
+  const AlphaRange ar = alpha_range(s, d, lo, hi);
+  const float span = ar.amax - ar.amin;
+  const float w = step_weight(p.step_mode, span, np);
+
+  // all sums carry the upstream gradient of the sample's channel
+  float sumV = 0.f;
+  float A[3] = {0.f, 0.f, 0.f}, Bv[3] = {0.f, 0.f, 0.f}, T = 0.f, Q = 0.f;
+  if (!misses_padded_box(s, d, p.vol)) {
+    const float lstep = 1.0f / (float)(np - 1);
+#pragma unroll 4
+    for (int k = 0; k < np; ++k) {
+      const float u = linspace01(k, np, lstep);
+      const float alpha = fmaf(u, span, ar.amin);
+      const float x = fmaf(alpha, d[0], s[0]);
+      const float y = fmaf(alpha, d[1], s[1]);
+      const float z = fmaf(alpha, d[2], s[2]);
+      float g[3];
+      const float v = sample_trilinear<true>(p.vol, x, y, z, g);
+      float go = g1;
+      if (LABELS) go = chan_g[sample_label(p.labels, p.vol, x, y, z) * 256 + tid];
+      sumV = fmaf(go, v, sumV);
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        const float ga = go * g[a];
+        g[a] = ga;
+        A[a] += ga;
+        Bv[a] = fmaf(alpha, ga, Bv[a]);
+      }
+      const float gd = fmaf(g[0], d[0], fmaf(g[1], d[1], g[2] * d[2]));
+      T += gd;
+      Q = fmaf(u, gd, Q);
+    }
+  }
+  const float P = T - Q;
+  const float wp = step_weight_dspan(p.step_mode, np);
+  float js[3], jt[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    js[a] = w * (A[a] - Bv[a]);
+    jt[a] = w * Bv[a];
+  }
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    if (ar.axis_min == a) {
+      const float dads = (ar.amin - 1.f) / d[a], dadt = -ar.amin / d[a];
+      js[a] += (w * P - sumV * wp) * dads;
+      jt[a] += (w * P - sumV * wp) * dadt;
+    }
+    if (ar.axis_max == a) {
+      const float dads = (ar.amax - 1.f) / d[a], dadt = -ar.amax / d[a];
+      js[a] += (w * Q + sumV * wp) * dads;
+      jt[a] += (w * Q + sumV * wp) * dadt;
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    p.gtarget[ray * 3 + a] = L * jt[a];
+    p.gsrc_ray[((int64_t)b * 3 + a) * p.N + n] = L * js[a];
+  }
+  p.graylen[ray] = sumV * w;
+}
+
+// Backward through a saved Jacobian: gtarget = g * J_t, gsrc_ray = g * J_s, graylen = g * J_L.
+__global__ void __launch_bounds__(256)
+jac_bwd_kernel(const float* __restrict__ jac, const float* __restrict__ gout, int B, int N,
+               float* __restrict__ gtarget, float* __restrict__ gsrc_ray, float* __restrict__ graylen) {
+  const int64_t ray = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (ray >= (int64_t)B * N) return;
+  const int b = (int)(ray / N);
+  const int n = (int)(ray - (int64_t)b * N);
+  const float g = __ldg(gout + ray);
+  const float* j = jac + (int64_t)b * 7 * N + n;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    gsrc_ray[((int64_t)b * 3 + a) * N + n] = g * __ldg(j + (int64_t)a * N);
+    gtarget[ray * 3 + a] = g * __ldg(j + (int64_t)(3 + a) * N);
+  }
+  graylen[ray] = g * __ldg(j + (int64_t)6 * N);
+}
+
+// Deterministic row sums: out[r] = sum_n in[r, n]; one CTA per row, fixed summation tree.
+__global__ void __launch_bounds__(1024) reduce_rows_kernel(const float* __restrict__ in, int N,
+                                                           float* __restrict__ out) {
+  __shared__ float part[32];
+  const float* row = in + (int64_t)blockIdx.x * N;
+  float acc = 0.f;
+  for (int n = threadIdx.x; n < N; n += 1024) acc += __ldg(row + n);
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = part[threadIdx.x];
+    v = warp_sum(v);
+    if (threadIdx.x == 0) out[blockIdx.x] = v;
+  }
+}
+
+static int fill_map(TileMap& m, int N, int det_h, int det_w, int lane_w_log2, int cta_w_log2, int* tiles) {
+  if (det_w > 0 && det_h > 0) {
+    if ((int64_t)det_h * det_w != N) {
+      set_last_error("detector hint H*W != N");
+      return XVR_ERR_INVALID;
+    }
+    if (lane_w_log2 < 0 || lane_w_log2 > 5 || cta_w_log2 < lane_w_log2 || cta_w_log2 > 8 ||
+        (8 - cta_w_log2) < (5 - lane_w_log2)) {
+      set_last_error("invalid tile shape");
+      return XVR_ERR_INVALID;
+    }
+    m.W = det_w;
+    m.H = det_h;
+    m.lane_w_log2 = lane_w_log2;
+    m.cta_w_log2 = cta_w_log2;
+    const int tw = 1 << cta_w_log2, th = 256 >> cta_w_log2;
+    m.tiles_x = (det_w + tw - 1) / tw;
+    m.tiles_y = (det_h + th - 1) / th;
+    *tiles = m.tiles_x * m.tiles_y;
+  } else {
+    m.W = 0;
+    m.H = 0;
+    m.lane_w_log2 = 5;
+    m.cta_w_log2 = 8;
+    m.tiles_x = (N + 255) / 256;
+    m.tiles_y = 1;
+    *tiles = m.tiles_x;
+  }
+  return XVR_OK;
+}
+
+static int fill_common(TrilinearParams& p, const float* volume, int D0, int D1, int D2, const uint8_t* labels,
+                       int C, const float* source, const float* target, const float* raylen, int B, int N,
+                       int n_points, int step_mode, float eps, int det_h, int det_w, int lane_w_log2,
+                       int cta_w_log2) {
+  if (!volume || !source || !target || !raylen || B <= 0 || N <= 0 || D0 < 2 || D1 < 2 || D2 < 2 ||
+      n_points < 2 || step_mode < 0 || step_mode > 2 || C < 1 || (labels && C > 255) || (!labels && C != 1)) {
+    set_last_error("xvr_trilinear: invalid argument");
+    return XVR_ERR_INVALID;
+  }
+  if ((int64_t)D0 * D1 * D2 >= (int64_t)1 << 31) {
+    set_last_error("xvr_trilinear: volume too large for 32-bit voxel offsets");
+    return XVR_ERR_INVALID;
+  }
+  p.vol.data = volume;
+  p.vol.D0 = D0;
+  p.vol.D1 = D1;
+  p.vol.D2 = D2;
+  p.vol.s0 = D1 * D2;
+  p.vol.s1 = D2;
+  p.labels = labels;
+  p.C = C;
+  p.source = source;
+  p.target = target;
+  p.raylen = raylen;
+  p.B = B;
+  p.N = N;
+  p.n_points = n_points;
+  p.step_mode = step_mode;
+  p.eps = eps;
+  return fill_map(p.map, N, det_h, det_w, lane_w_log2, cta_w_log2, &p.tiles_per_pose);
+}
+
+}  // namespace xvr
+
+using namespace xvr;
+
+extern "C" int xvr_trilinear_rays_fwd(const float* volume, int D0, int D1, int D2, const uint8_t* labels, int C,
+                                      const float* source, const float* target, const float* raylen, int B,
+                                      int N, int n_points, int step_mode, float eps, int det_h, int det_w,
+                                      int lane_w_log2, int cta_w_log2, float* out, float* jac, void* stream) {
+  TrilinearParams p = {};
+  int rc = fill_common(p, volume, D0, D1, D2, labels, C, source, target, raylen, B, N, n_points, step_mode, eps,
+                       det_h, det_w, lane_w_log2, cta_w_log2);
+  if (rc) return rc;
+  if (!out || (jac && labels)) {
+    set_last_error("xvr_trilinear_rays_fwd: out is null, or jac requested together with labels");
+    return XVR_ERR_INVALID;
+  }
+  p.out = out;
+  p.jac = jac;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t grid = (int64_t)B * p.tiles_per_pose;
+  if (grid >= (int64_t)1 << 31) {
+    set_last_error("xvr_trilinear_rays_fwd: grid too large");
+    return XVR_ERR_INVALID;
+  }
+  const size_t smem = labels ? (size_t)C * 256 * sizeof(float) : 0;
+  if (labels) {
+    if (smem > 48 * 1024) {
+      cudaFuncSetAttribute(trilinear_fwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)smem);
+    }
+    trilinear_fwd_kernel<false, true><<<(unsigned)grid, 256, smem, st>>>(p);
+  } else {
+    if (jac) trilinear_fwd_kernel<true, false><<<(unsigned)grid, 256, 0, st>>>(p);
+    else trilinear_fwd_kernel<false, false><<<(unsigned)grid, 256, 0, st>>>(p);
+  }
+  return check_launch("xvr_trilinear_rays_fwd");
+}
+
+extern "C" int xvr_trilinear_rays_bwd(const float* volume, int D0, int D1, int D2, const uint8_t* labels, int C,
+                                      const float* source, const float* target, const float* raylen, int B,
+                                      int N, int n_points, int step_mode, float eps, int det_h, int det_w,
+                                      int lane_w_log2, int cta_w_log2, const float* gout, float* gsource,
+                                      float* gtarget, float* graylen, float* workspace, void* stream) {
+  TrilinearParams p = {};
+  int rc = fill_common(p, volume, D0, D1, D2, labels, C, source, target, raylen, B, N, n_points, step_mode, eps,
+                       det_h, det_w, lane_w_log2, cta_w_log2);
+  if (rc) return rc;
+  if (!gout || !gsource || !gtarget || !graylen || !workspace) {
+    set_last_error("xvr_trilinear_rays_bwd: null gradient buffer");
+    return XVR_ERR_INVALID;
+  }
+  p.gout = gout;
+  p.gtarget = gtarget;
+  p.gsrc_ray = workspace;  // (B,3,N)
+  p.graylen = graylen;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t grid = (int64_t)B * p.tiles_per_pose;
+  const size_t smem = labels ? (size_t)C * 256 * sizeof(float) : 0;
+  if (labels) {
+    if (smem > 48 * 1024)
+      cudaFuncSetAttribute(trilinear_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    trilinear_bwd_kernel<true><<<(unsigned)grid, 256, smem, st>>>(p);
+  } else {
+    trilinear_bwd_kernel<false><<<(unsigned)grid, 256, 0, st>>>(p);
+  }
+  rc = check_launch("xvr_trilinear_rays_bwd");
+  if (rc) return rc;
+  reduce_rows_kernel<<<B * 3, 1024, 0, st>>>(workspace, N, gsource);
+  return check_launch("xvr_trilinear_rays_bwd/reduce");
+}
+
+extern "C" int xvr_rays_jac_bwd(const float* jac, const float* gout, int B, int N, float* gsource,
+                                float* gtarget, float* graylen, float* workspace, void* stream) {
+  if (!jac || !gout || !gsource || !gtarget || !graylen || !workspace || B <= 0 || N <= 0) {
+    set_last_error("xvr_rays_jac_bwd: invalid argument");
+    return XVR_ERR_INVALID;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t rays = (int64_t)B * N;
+  jac_bwd_kernel<<<(unsigned)((rays + 255) / 256), 256, 0, st>>>(jac, gout, B, N, gtarget, workspace, graylen);
+  int rc = check_launch("xvr_rays_jac_bwd");
+  if (rc) return rc;
+  reduce_rows_kernel<<<B * 3, 1024, 0, st>>>(workspace, N, gsource);
+  return check_launch("xvr_rays_jac_bwd/reduce");
+}
