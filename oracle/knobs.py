@@ -8,6 +8,13 @@ parity suite then re-checks kernels against the corrected oracle.
 # A1: A.compose(B) applies A first, then B  ->  B.matrix @ A.matrix
 COMPOSE_APPLIES_SELF_FIRST = True
 
+# A2: convert(rot, xyz) places the camera centre in the ROTATED frame: matrix = [R | R @ xyz], so that changing
+# the angles orbits the C-arm about the isocenter (xvr's sampler draws ty in [700, 900] mm with +-45 deg
+# rotations and expects the volume to stay in view; /root/reference/src/xvr/utils/ants.py:71-82 rebuilds a pose
+# as make_matrix(R, R @ (A^-1 t)), i.e. make_matrix itself is a plain [R | t] assembler).
+# RigidTransform.convert returns xyz = R^T t.  (se3_log_map carries its own translation coupling.)
+CONVERT_TRANSLATION_IN_ROTATED_FRAME = True
+
 # A3: detector pixel (row i, col j) -> camera-frame point
 #   x = DET_SIGN_S * (j - W//2 + off_w) * delx + x0     (sign flipped by reverse_x_axis)
 #   y = DET_SIGN_T * (i - H//2 + off_h) * dely + y0

@@ -278,12 +278,16 @@ def pose_from_params(rot, xyz, parameterization, convention=None, degrees=False)
         R = quaternion_to_matrix(quaternion_adjugate_to_quaternion(rot))
     else:
         raise ValueError(parameterization)
+    if knobs.CONVERT_TRANSLATION_IN_ROTATED_FRAME and parameterization != "se3_log_map":
+        xyz = (R @ xyz[..., None])[..., 0]
     return make_matrix(R, xyz)
 
 
 def params_from_pose(M, parameterization, convention=None, degrees=False):
     """RigidTransform.convert(parameterization, convention) -> (rot, xyz)."""
     R, t = M[..., :3, :3], M[..., :3, 3]
+    if knobs.CONVERT_TRANSLATION_IN_ROTATED_FRAME and parameterization != "se3_log_map":
+        t = (R.transpose(-1, -2) @ t[..., None])[..., 0]
     if parameterization == "euler_angles":
         rot = matrix_to_euler_angles(R, convention)
         if degrees:

@@ -9,6 +9,11 @@ correction is made in exactly two places and re-checked by the parity suite.
 # RigidTransform.compose: A.compose(B) applies A first, then B -> B.matrix @ A.matrix
 COMPOSE_APPLIES_SELF_FIRST = True
 
+# convert(rot, xyz): the camera centre is given in the rotated frame, matrix = [R | R @ xyz] (angles orbit the
+# C-arm about the isocenter); RigidTransform.convert returns xyz = R^T t.  make_matrix is a plain assembler
+# (/root/reference/src/xvr/utils/ants.py:71-82).  se3_log_map keeps its own translation coupling.
+CONVERT_TRANSLATION_IN_ROTATED_FRAME = True
+
 # Detector pixel (row i, col j) -> camera-frame point (x, y, z) =
 #   (DET_SIGN_S * (j - W//2 + off_w) * delx + x0, DET_SIGN_T * (i - H//2 + off_h) * dely + y0, sdd)
 # with DET_SIGN_S negated by reverse_x_axis.

@@ -223,6 +223,8 @@ def convert(*args, parameterization, convention=None, degrees=False):
         raise TypeError("convert(rot, xyz, parameterization=..., convention=...)")
     rot, xyz = args
     R, t = _rotation(rot, xyz, parameterization, convention, degrees)
+    if conv.CONVERT_TRANSLATION_IN_ROTATED_FRAME and parameterization != "se3_log_map":
+        t = (R @ t[..., None])[..., 0]
     return RigidTransform(make_matrix(R, t))
 
 
@@ -276,6 +278,8 @@ class RigidTransform(torch.nn.Module):
     def convert(self, parameterization, convention=None, degrees=False):
         """Inverse of :func:`convert`: ``-> (rot, xyz)``."""
         R, t = self.rotation, self.translation
+        if conv.CONVERT_TRANSLATION_IN_ROTATED_FRAME and parameterization != "se3_log_map":
+            t = (R.transpose(-1, -2) @ t[..., None])[..., 0]
         if parameterization == "euler_angles":
             rot = matrix_to_euler_angles(R, convention)
             rot = torch.rad2deg(rot) if degrees else rot
