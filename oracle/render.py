@@ -180,7 +180,9 @@ def siddon_render(volume, source, target, raylen, mask=None, voxel_shift=None, e
     alphas = siddon_alphas(source, target, tuple(volume.shape), vs, eps)
     alphamid = (alphas[..., 0:-1] + alphas[..., 1:]) / 2
     grid = _siddon_grid(alphamid, source, target, tuple(volume.shape), vs, eps)
-    grid = torch.nan_to_num(grid, nan=-2.0)  # NaN midpoints -> out of bounds -> zero padding
+    # NaN midpoints -> out of bounds -> zero padding.  Nearest-neighbour lookups have a zero gradient w.r.t. the
+    # grid; detaching states that directly (autograd would otherwise form 0 * NaN = NaN on the padded columns).
+    grid = torch.nan_to_num(grid, nan=-2.0).detach()
     voxels = _voxel(volume, grid, "nearest", knobs.SIDDON_ALIGN_CORNERS)
     seg = torch.diff(alphas, dim=-1)
     weighted = torch.nan_to_num(voxels * seg, nan=0.0)

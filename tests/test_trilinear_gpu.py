@@ -141,10 +141,44 @@ def test_jacobian_and_recompute_backward_agree(cuda):
     gs, gt, gl, work = (torch.empty(B, 1, 3, device=cuda), torch.empty(B, N, 3, device=cuda),
                         torch.empty(B, 1, N, device=cuda), torch.empty(B, 3, N, device=cuda))
     vol = drr.density
-    call("xvr_trilinear_rays_bwd", ptr(vol), *vol.shape, None, 1, ptr(source), ptr(target), ptr(raylen), B, N, 500,
+    call("xvr_trilinear_rays_bwd", ptr(vol), None, *vol.shape, None, 1, ptr(source), ptr(target), ptr(raylen), B, N, 500,
          0, 1e-8, 32, 32, 3, 4, ptr(gout), ptr(gs), ptr(gt), ptr(gl), ptr(work), stream())
     assert rel_l2(gs, s.grad) < 1e-5
     assert rel_l2(gt, t.grad) < 1e-5
+
+
+def test_texture_and_linear_gathers_agree_bitwise(cuda, monkeypatch):
+    """The TLD4 path fetches the same fp32 texels as the scalar-load path: images and gradients are identical."""
+    drr = make_drr(64, 32)
+    rot, xyz = pose_params(3, seed=9)
+    res = []
+    for mode in ("tex", "ldg"):
+        monkeypatch.setenv("XVR_B200_GATHER", mode)
+        r, x = rot.clone().requires_grad_(), xyz.clone().requires_grad_()
+        img = _render(drr, r, x)
+        img.sum().backward()
+        res.append((img.detach(), r.grad, x.grad))
+    for a, b in zip(*res):
+        assert torch.equal(a, b)
+
+
+def test_texture_tracks_volume_updates(cuda):
+    """A new or in-place-modified volume tensor must be re-uploaded to the texture (trainer.py:196-197)."""
+    drr = make_drr(48, 24)
+    rot, xyz = pose_params(2, seed=10)
+    img0 = _render(drr, rot, xyz)
+    drr.density.mul_(2.0)
+    img1 = _render(drr, rot, xyz)
+    assert rel_l2(img1, 2 * img0) < 1e-6
+    pose = xvr_b200.convert(rot, xyz, parameterization="euler_angles", convention="ZXY")
+    source, target = drr.detector(pose, None)
+    raylen = (target - source).norm(dim=-1).unsqueeze(1)
+    source, target = drr.affine_inverse(source), drr.affine_inverse(target)
+    for scale in (3.0, 5.0):
+        tmp = drr.density * scale  # fresh tensor every step, possibly at a recycled address
+        img = drr.renderer(tmp, source, target, raylen).view_as(img1)
+        assert rel_l2(img, scale * img1) < 1e-6
+        del tmp
 
 
 def test_tile_shapes_give_identical_images(cuda, monkeypatch):
@@ -162,9 +196,8 @@ def test_errors_are_loud(cuda):
     drr = make_drr(32, 16)
     rot, xyz = pose_params(1)
     pose = xvr_b200.convert(rot, xyz, parameterization="euler_angles", convention="ZXY")
-    with pytest.raises(xvr_b200._lib.XvrB200Error):
-        drr.cpu()(pose.cpu())  # no CPU path
-    drr = drr.cuda()
     source, target = drr.detector(pose, None)
+    with pytest.raises(xvr_b200._lib.XvrB200Error):  # no CPU path
+        drr.renderer(drr.density.cpu(), source.cpu(), target.cpu(), torch.ones(1, 1, 256))
     with pytest.raises(ValueError):
         drr.renderer(drr.density, source, target, torch.ones(1, 1, 3, device=cuda))

@@ -18,13 +18,25 @@ _SIGNATURES = {
     "xvr_abi_version": ([], c_int),
     "xvr_last_error": ([], ctypes.c_char_p),
     "xvr_launch_count": ([], c_int64),
+    "xvr_volume_create": ([c_int, c_int, c_int, ctypes.POINTER(c_void_p)], c_int),
+    "xvr_volume_upload": ([P, P, P], c_int),
+    "xvr_volume_destroy": ([P], c_int),
     "xvr_trilinear_rays_fwd": (
-        [P, c_int, c_int, c_int, P, c_int, P, P, P, c_int, c_int, c_int, c_int, c_float, c_int, c_int, c_int,
+        [P, P, c_int, c_int, c_int, P, c_int, P, P, P, c_int, c_int, c_int, c_int, c_float, c_int, c_int, c_int,
          c_int, P, P, P], c_int),
     "xvr_trilinear_rays_bwd": (
-        [P, c_int, c_int, c_int, P, c_int, P, P, P, c_int, c_int, c_int, c_int, c_float, c_int, c_int, c_int,
+        [P, P, c_int, c_int, c_int, P, c_int, P, P, P, c_int, c_int, c_int, c_int, c_float, c_int, c_int, c_int,
          c_int, P, P, P, P, P, P], c_int),
     "xvr_rays_jac_bwd": ([P, P, c_int, c_int, P, P, P, P, P], c_int),
+    "xvr_reduce_rows": ([P, c_int, c_int, P, P], c_int),
+    "xvr_siddon_rays_fwd": (
+        [P, c_int, c_int, c_int, P, c_int, P, P, P, c_int, c_int, c_float, c_float, c_int, c_int, c_int, c_int, P, P,
+         P], c_int),
+    "xvr_siddon_rays_bwd": (
+        [P, c_int, c_int, c_int, P, c_int, P, P, P, c_int, c_int, c_float, c_float, c_int, c_int, c_int, c_int, P, P,
+         P, P, P, P], c_int),
+    "xvr_siddon_trace": (
+        [P, c_int, c_int, c_int, P, P, c_int, c_int, c_float, c_float, c_int, P, P, P, P], c_int),
 }
 
 

@@ -32,3 +32,73 @@ extern "C" int xvr_abi_version(void) { return 1; }
 
 // Number of kernels this library has launched since load (bench.py's gpu_launches evidence).
 extern "C" long long xvr_launch_count(void) { return xvr::g_launches; }
+
+// ---------------------------------------------------------------------------------------------- volume texture
+// A second, block-linear copy of the CT volume (cudaArray, layered 2D: layer = axis 0) behind a point-sampled
+// texture object.  The trilinear kernels fetch the 2x2 (axis 1, axis 2) corner footprint of each of the two
+// layers with one TLD4 each instead of 8 scalar loads.
+extern "C" int xvr_volume_create(int D0, int D1, int D2, void** out) {
+  if (!out || D0 < 1 || D1 < 1 || D2 < 1 || D0 > 2048 || D1 > 32768 || D2 > 32768) {
+    xvr::set_last_error("xvr_volume_create: invalid shape (layered 2D arrays hold <= 2048 layers of <= 32768^2)");
+    return XVR_ERR_INVALID;
+  }
+  xvr::VolumeTexture* vt = new xvr::VolumeTexture();
+  vt->D0 = D0;
+  vt->D1 = D1;
+  vt->D2 = D2;
+  cudaChannelFormatDesc desc = cudaCreateChannelDesc<float>();
+  cudaError_t e = cudaMalloc3DArray(&vt->array, &desc, make_cudaExtent(D2, D1, D0), cudaArrayLayered);
+  if (e == cudaSuccess) {
+    cudaResourceDesc rd = {};
+    rd.resType = cudaResourceTypeArray;
+    rd.res.array.array = vt->array;
+    cudaTextureDesc td = {};
+    td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeBorder;
+    td.filterMode = cudaFilterModePoint;
+    td.readMode = cudaReadModeElementType;
+    td.normalizedCoords = 0;
+    e = cudaCreateTextureObject(&vt->tex, &rd, &td, nullptr);
+    if (e != cudaSuccess) cudaFreeArray(vt->array);
+  }
+  if (e != cudaSuccess) {
+    char msg[256];
+    snprintf(msg, sizeof(msg), "xvr_volume_create: %s", cudaGetErrorString(e));
+    xvr::set_last_error(msg);
+    cudaGetLastError();
+    delete vt;
+    return XVR_ERR_CUDA;
+  }
+  *out = vt;
+  return XVR_OK;
+}
+
+extern "C" int xvr_volume_upload(void* handle, const float* volume, void* stream) {
+  xvr::VolumeTexture* vt = (xvr::VolumeTexture*)handle;
+  if (!vt || !volume) {
+    xvr::set_last_error("xvr_volume_upload: null argument");
+    return XVR_ERR_INVALID;
+  }
+  cudaMemcpy3DParms cp = {};
+  cp.srcPtr = make_cudaPitchedPtr((void*)volume, (size_t)vt->D2 * sizeof(float), vt->D2, vt->D1);
+  cp.dstArray = vt->array;
+  cp.extent = make_cudaExtent(vt->D2, vt->D1, vt->D0);
+  cp.kind = cudaMemcpyDeviceToDevice;
+  cudaError_t e = cudaMemcpy3DAsync(&cp, (cudaStream_t)stream);
+  if (e != cudaSuccess) {
+    char msg[256];
+    snprintf(msg, sizeof(msg), "xvr_volume_upload: %s", cudaGetErrorString(e));
+    xvr::set_last_error(msg);
+    cudaGetLastError();
+    return XVR_ERR_CUDA;
+  }
+  return XVR_OK;
+}
+
+extern "C" int xvr_volume_destroy(void* handle) {
+  xvr::VolumeTexture* vt = (xvr::VolumeTexture*)handle;
+  if (!vt) return XVR_OK;
+  cudaDestroyTextureObject(vt->tex);
+  cudaFreeArray(vt->array);
+  delete vt;
+  return XVR_OK;
+}

@@ -20,7 +20,27 @@ struct Vol {
   const float* __restrict__ data;
   int D0, D1, D2;
   int s0, s1;  // element strides of axis 0 / 1 (D1*D2, D2)
+  cudaTextureObject_t tex;  // optional layered-2D copy: layer = axis 0, height = axis 1, width = axis 2
 };
+
+// Opaque handle behind xvr_volume_* (include/xvr_b200.h): a block-linear layered array + point-sampled texture.
+struct VolumeTexture {
+  cudaArray_t array;
+  cudaTextureObject_t tex;
+  int D0, D1, D2;
+};
+
+// The 2x2 (axis1, axis2) footprint around texel-corner (u, v) of one layer in a single TEX instruction.
+// With u = iz + 1, v = iy + 1 the request sits exactly between four texel centres, so the footprint selection is
+// not subject to the sampler's fixed-point coordinate rounding; the returned values are the stored fp32 texels
+// (.x = (iy+1, iz), .y = (iy+1, iz+1), .z = (iy, iz+1), .w = (iy, iz)); out-of-range texels read 0 (border mode).
+__device__ __forceinline__ float4 gather_yz(cudaTextureObject_t tex, int layer, float u, float v) {
+  float4 r;
+  asm volatile("tld4.r.a2d.v4.f32.f32 {%0,%1,%2,%3}, [%4, {%5,%6,%7,%7}];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(tex), "r"(layer), "f"(u), "f"(v));
+  return r;
+}
 
 // Slab test of the segment s + alpha*d, alpha in [0,1], against the box [lo, hi]^3 (per axis).
 // Restates DiffDRR renderers._get_alpha_minmax: per-axis (plane - s)/d with IEEE division, min/max over the
@@ -66,13 +86,21 @@ __device__ __forceinline__ float linspace01(int k, int n, float step) {
 // ATen/native/cuda/GridSampler.cuh:23-31 and the out-of-bounds handling at :225-227).
 // GRAD additionally returns the spatial gradient dV/dx (zero-padded corners differentiate as zeros,
 // which is what grid_sampler_3d_backward computes).
-template <bool GRAD>
+template <bool GRAD, bool TEX>
 __device__ __forceinline__ float sample_trilinear(const Vol& v, float x, float y, float z, float g[3]) {
   float fx0 = floorf(x), fy0 = floorf(y), fz0 = floorf(z);
   int ix = (int)fx0, iy = (int)fy0, iz = (int)fz0;
   float fx = x - fx0, fy = y - fy0, fz = z - fz0;
   float c000, c001, c010, c011, c100, c101, c110, c111;
-  if ((unsigned)ix < (unsigned)(v.D0 - 1) && (unsigned)iy < (unsigned)(v.D1 - 1) &&
+  if (TEX) {
+    // two gathers fetch the 8 corners; axis-1/2 padding comes from the border mode, axis-0 from the predicates
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    const float tu = fz0 + 1.0f, tv = fy0 + 1.0f;
+    if ((unsigned)ix < (unsigned)v.D0) a = gather_yz(v.tex, ix, tu, tv);
+    if ((unsigned)(ix + 1) < (unsigned)v.D0) b = gather_yz(v.tex, ix + 1, tu, tv);
+    c010 = a.x; c011 = a.y; c001 = a.z; c000 = a.w;
+    c110 = b.x; c111 = b.y; c101 = b.z; c100 = b.w;
+  } else if ((unsigned)ix < (unsigned)(v.D0 - 1) && (unsigned)iy < (unsigned)(v.D1 - 1) &&
       (unsigned)iz < (unsigned)(v.D2 - 1)) {
     const float* p = v.data + ((int64_t)ix * v.s0 + iy * v.s1 + iz);
     c000 = __ldg(p);

@@ -53,7 +53,7 @@ __device__ __forceinline__ bool misses_padded_box(const float s[3], const float 
   return !(r.amin < r.amax);
 }
 
-template <bool JAC, bool LABELS>
+template <bool JAC, bool LABELS, bool TEX>
 __global__ void __launch_bounds__(256) trilinear_fwd_kernel(const TrilinearParams p) {
   extern __shared__ float chan_acc[];  // LABELS: [C][256]
   const int b = blockIdx.x / p.tiles_per_pose;
@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(256) trilinear_fwd_kernel(const TrilinearParam
       const float y = fmaf(alpha, d[1], s[1]);
       const float z = fmaf(alpha, d[2], s[2]);
       float g[3];
-      const float v = sample_trilinear<JAC>(p.vol, x, y, z, g);
+      const float v = sample_trilinear<JAC, TEX>(p.vol, x, y, z, g);
       if (LABELS) {
         const int c = sample_label(p.labels, p.vol, x, y, z);
         chan_acc[c * 256 + tid] += v;
@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(256) trilinear_fwd_kernel(const TrilinearParam
 // Recompute backward: given dL/dout (B,C,N) re-march every ray and emit dL/dtarget (B,N,3), the per-ray
 // dL/dsource (B,3,N) and dL/draylen (B,N).  Handles label channels (the upstream gradient of a sample is the
 // one of the channel its label selects).
-template <bool LABELS>
+template <bool LABELS, bool TEX>
 __global__ void __launch_bounds__(256) trilinear_bwd_kernel(const TrilinearParams p) {
   extern __shared__ float chan_g[];  // LABELS: [C][256] upstream gradient per channel
   const int b = blockIdx.x / p.tiles_per_pose;
@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(256) trilinear_bwd_kernel(const TrilinearParam
       const float y = fmaf(alpha, d[1], s[1]);
       const float z = fmaf(alpha, d[2], s[2]);
       float g[3];
-      const float v = sample_trilinear<true>(p.vol, x, y, z, g);
+      const float v = sample_trilinear<true, TEX>(p.vol, x, y, z, g);
       float go = g1;
       if (LABELS) go = chan_g[sample_label(p.labels, p.vol, x, y, z) * 256 + tid];
       sumV = fmaf(go, v, sumV);
@@ -318,7 +318,8 @@ static int fill_map(TileMap& m, int N, int det_h, int det_w, int lane_w_log2, in
   return XVR_OK;
 }
 
-static int fill_common(TrilinearParams& p, const float* volume, int D0, int D1, int D2, const uint8_t* labels,
+static int fill_common(TrilinearParams& p, const float* volume, const void* voltex, int D0, int D1, int D2,
+                       const uint8_t* labels,
                        int C, const float* source, const float* target, const float* raylen, int B, int N,
                        int n_points, int step_mode, float eps, int det_h, int det_w, int lane_w_log2,
                        int cta_w_log2) {
@@ -337,6 +338,15 @@ static int fill_common(TrilinearParams& p, const float* volume, int D0, int D1, 
   p.vol.D2 = D2;
   p.vol.s0 = D1 * D2;
   p.vol.s1 = D2;
+  p.vol.tex = 0;
+  if (voltex) {
+    const VolumeTexture* vt = (const VolumeTexture*)voltex;
+    if (vt->D0 != D0 || vt->D1 != D1 || vt->D2 != D2) {
+      set_last_error("xvr_trilinear: volume texture shape differs from the volume");
+      return XVR_ERR_INVALID;
+    }
+    p.vol.tex = vt->tex;
+  }
   p.labels = labels;
   p.C = C;
   p.source = source;
@@ -354,12 +364,13 @@ static int fill_common(TrilinearParams& p, const float* volume, int D0, int D1, 
 
 using namespace xvr;
 
-extern "C" int xvr_trilinear_rays_fwd(const float* volume, int D0, int D1, int D2, const uint8_t* labels, int C,
+extern "C" int xvr_trilinear_rays_fwd(const float* volume, const void* voltex, int D0, int D1, int D2,
+                                      const uint8_t* labels, int C,
                                       const float* source, const float* target, const float* raylen, int B,
                                       int N, int n_points, int step_mode, float eps, int det_h, int det_w,
                                       int lane_w_log2, int cta_w_log2, float* out, float* jac, void* stream) {
   TrilinearParams p = {};
-  int rc = fill_common(p, volume, D0, D1, D2, labels, C, source, target, raylen, B, N, n_points, step_mode, eps,
+  int rc = fill_common(p, volume, voltex, D0, D1, D2, labels, C, source, target, raylen, B, N, n_points, step_mode, eps,
                        det_h, det_w, lane_w_log2, cta_w_log2);
   if (rc) return rc;
   if (!out || (jac && labels)) {
@@ -375,26 +386,29 @@ extern "C" int xvr_trilinear_rays_fwd(const float* volume, int D0, int D1, int D
     return XVR_ERR_INVALID;
   }
   const size_t smem = labels ? (size_t)C * 256 * sizeof(float) : 0;
+  const bool tex = p.vol.tex != 0;
   if (labels) {
-    if (smem > 48 * 1024) {
-      cudaFuncSetAttribute(trilinear_fwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)smem);
-    }
-    trilinear_fwd_kernel<false, true><<<(unsigned)grid, 256, smem, st>>>(p);
+    auto k = tex ? trilinear_fwd_kernel<false, true, true> : trilinear_fwd_kernel<false, true, false>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k<<<(unsigned)grid, 256, smem, st>>>(p);
+  } else if (jac) {
+    auto k = tex ? trilinear_fwd_kernel<true, false, true> : trilinear_fwd_kernel<true, false, false>;
+    k<<<(unsigned)grid, 256, 0, st>>>(p);
   } else {
-    if (jac) trilinear_fwd_kernel<true, false><<<(unsigned)grid, 256, 0, st>>>(p);
-    else trilinear_fwd_kernel<false, false><<<(unsigned)grid, 256, 0, st>>>(p);
+    auto k = tex ? trilinear_fwd_kernel<false, false, true> : trilinear_fwd_kernel<false, false, false>;
+    k<<<(unsigned)grid, 256, 0, st>>>(p);
   }
   return check_launch("xvr_trilinear_rays_fwd");
 }
 
-extern "C" int xvr_trilinear_rays_bwd(const float* volume, int D0, int D1, int D2, const uint8_t* labels, int C,
+extern "C" int xvr_trilinear_rays_bwd(const float* volume, const void* voltex, int D0, int D1, int D2,
+                                      const uint8_t* labels, int C,
                                       const float* source, const float* target, const float* raylen, int B,
                                       int N, int n_points, int step_mode, float eps, int det_h, int det_w,
                                       int lane_w_log2, int cta_w_log2, const float* gout, float* gsource,
                                       float* gtarget, float* graylen, float* workspace, void* stream) {
   TrilinearParams p = {};
-  int rc = fill_common(p, volume, D0, D1, D2, labels, C, source, target, raylen, B, N, n_points, step_mode, eps,
+  int rc = fill_common(p, volume, voltex, D0, D1, D2, labels, C, source, target, raylen, B, N, n_points, step_mode, eps,
                        det_h, det_w, lane_w_log2, cta_w_log2);
   if (rc) return rc;
   if (!gout || !gsource || !gtarget || !graylen || !workspace) {
@@ -408,17 +422,29 @@ extern "C" int xvr_trilinear_rays_bwd(const float* volume, int D0, int D1, int D
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t grid = (int64_t)B * p.tiles_per_pose;
   const size_t smem = labels ? (size_t)C * 256 * sizeof(float) : 0;
+  const bool tex = p.vol.tex != 0;
   if (labels) {
-    if (smem > 48 * 1024)
-      cudaFuncSetAttribute(trilinear_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    trilinear_bwd_kernel<true><<<(unsigned)grid, 256, smem, st>>>(p);
+    auto k = tex ? trilinear_bwd_kernel<true, true> : trilinear_bwd_kernel<true, false>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k<<<(unsigned)grid, 256, smem, st>>>(p);
   } else {
-    trilinear_bwd_kernel<false><<<(unsigned)grid, 256, 0, st>>>(p);
+    auto k = tex ? trilinear_bwd_kernel<false, true> : trilinear_bwd_kernel<false, false>;
+    k<<<(unsigned)grid, 256, 0, st>>>(p);
   }
   rc = check_launch("xvr_trilinear_rays_bwd");
   if (rc) return rc;
   reduce_rows_kernel<<<B * 3, 1024, 0, st>>>(workspace, N, gsource);
   return check_launch("xvr_trilinear_rays_bwd/reduce");
+}
+
+// out[r] = sum_n in[r, n] with a fixed summation tree (deterministic); shared by the Siddon entry points.
+extern "C" int xvr_reduce_rows(const float* in, int rows, int N, float* out, void* stream) {
+  if (!in || !out || rows <= 0 || N <= 0) {
+    set_last_error("xvr_reduce_rows: invalid argument");
+    return XVR_ERR_INVALID;
+  }
+  reduce_rows_kernel<<<rows, 1024, 0, (cudaStream_t)stream>>>(in, N, out);
+  return check_launch("xvr_reduce_rows");
 }
 
 extern "C" int xvr_rays_jac_bwd(const float* jac, const float* gout, int B, int N, float* gsource,

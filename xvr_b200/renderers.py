@@ -6,7 +6,9 @@ with ``source``/``target`` in voxel-index coordinates.  The modules are autograd
 to ``source``, ``target``, ``raylen`` (pose path) and, on request, to ``volume``.
 """
 
+import ctypes
 import os
+import weakref
 
 import torch
 
@@ -18,12 +20,55 @@ __all__ = ["Trilinear", "Siddon"]
 
 
 def _tile_shape():
-    """(lane_w_log2, cta_w_log2): 8x4-pixel warps in 16x16-pixel CTAs unless overridden for tuning."""
+    """(lane_w_log2, cta_w_log2): each warp takes a 32-row x 1-column strip of detector pixels and a CTA eight
+    adjacent strips (detector rows run along the volume's contiguous axis in the usual AP/PA set-up), unless
+    overridden for tuning."""
     env = os.environ.get("XVR_B200_TILE")
     if env:
         lw, cw = (int(v) for v in env.split(","))
         return lw, cw
-    return 3, 4
+    return 0, 3
+
+
+class _VolumeTexture:
+    """Block-linear (layered cudaArray) copy of the volume behind a texture object, re-uploaded whenever the
+    source tensor is a different object or has been modified in place (torch's version counter)."""
+
+    def __init__(self):
+        self.handle = None
+        self.shape = None
+        self.device = None
+        self.src = None  # weakref to the tensor last uploaded
+        self.version = None
+
+    def get(self, volume):
+        if os.environ.get("XVR_B200_GATHER", "tex") != "tex":
+            return None
+        shape = tuple(volume.shape)
+        if self.handle is None or shape != self.shape or volume.device != self.device:
+            self.free()
+            h = ctypes.c_void_p()
+            with torch.cuda.device(volume.device):
+                call("xvr_volume_create", *shape, ctypes.byref(h))
+            self.handle, self.shape, self.device, self.src = h, shape, volume.device, None
+        if self.src is None or self.src() is not volume or self.version != volume._version:
+            call("xvr_volume_upload", self.handle, ptr(volume), stream())
+            self.src, self.version = weakref.ref(volume), volume._version
+        return self.handle
+
+    def __deepcopy__(self, memo):
+        return _VolumeTexture()  # device resources are per-instance: the copy re-creates its own lazily
+
+    def free(self):
+        if self.handle is not None:
+            try:
+                _lib.lib().xvr_volume_destroy(self.handle)
+            except Exception:  # noqa: BLE001 - interpreter shutdown
+                pass
+            self.handle = None
+
+    def __del__(self):
+        self.free()
 
 
 class _LabelCache:
@@ -33,6 +78,9 @@ class _LabelCache:
         self.key = None
         self.labels = None
         self.channels = 1
+
+    def __deepcopy__(self, memo):
+        return _LabelCache()
 
     def get(self, mask):
         key = (mask.data_ptr(), mask._version, tuple(mask.shape), mask.dtype, mask.device)
@@ -60,14 +108,21 @@ def _check_rays(volume, source, target, raylen):
     return B, N
 
 
-class _TrilinearRays(torch.autograd.Function):
+class _RenderRays(torch.autograd.Function):
+    """(volume, source, target, raylen) -> (B,C,N) through the C-ABI; ``kind`` selects the renderer and ``args``
+    holds its scalar arguments in C-ABI order (trilinear: n_points, step_mode, eps; siddon: voxel_shift, eps).
+
+    When pose gradients are needed and there are no label channels, the forward kernel also emits the per-ray
+    Jacobian d out / d(source, target, raylen) -- it does not depend on the upstream gradient -- so the backward
+    pass is a 28-byte-per-ray epilogue instead of a second march through the volume.
+    """
+
     @staticmethod
-    def forward(ctx, volume, source, target, raylen, labels, C, n_points, step_mode, eps, det_hw):
-        volume, source, target, raylen = (
-            cuda_f32(volume, "volume"), cuda_f32(source, "source"), cuda_f32(target, "target"),
-            cuda_f32(raylen, "raylen"))
+    def forward(ctx, volume, source, target, raylen, labels, C, kind, args, det_hw, voltex):
+        source, target, raylen = cuda_f32(source, "source"), cuda_f32(target, "target"), cuda_f32(raylen, "raylen")
         B, N = _check_rays(volume, source, target, raylen)
-        D0, D1, D2 = volume.shape
+        if ctx.needs_input_grad[0]:
+            raise _lib.XvrB200Error("d/dvolume is computed by xvr_b200.renderers.volume_gradient, not by autograd")
         lw, cw = _tile_shape()
         det_h, det_w = det_hw if det_hw is not None and det_hw[0] * det_hw[1] == N else (0, 0)
         need_pose_grad = any(ctx.needs_input_grad[1:4])
@@ -75,22 +130,21 @@ class _TrilinearRays(torch.autograd.Function):
         jac = None
         if need_pose_grad and labels is None:
             jac = torch.empty(B, 7, N, device=volume.device, dtype=torch.float32)
-        call("xvr_trilinear_rays_fwd", ptr(volume), D0, D1, D2, ptr(labels), C, ptr(source), ptr(target),
-             ptr(raylen), B, N, n_points, step_mode, eps, det_h, det_w, lw, cw, ptr(out), ptr(jac), stream())
-        ctx.cfg = (C, n_points, step_mode, eps, det_h, det_w, lw, cw)
+        vol_args = (ptr(volume),) if voltex is False else (ptr(volume), voltex)
+        ctx.common = (*vol_args, *volume.shape, ptr(labels), C, ptr(source), ptr(target), ptr(raylen), B, N, *args,
+                      det_h, det_w, lw, cw)
+        call(f"xvr_{kind}_rays_fwd", *ctx.common, ptr(out), ptr(jac), stream())
+        ctx.kind = kind
         if jac is not None:
             ctx.save_for_backward(jac)
             ctx.mode = "jac"
         elif need_pose_grad:
-            ctx.save_for_backward(volume, source, target, raylen, labels)
+            ctx.save_for_backward(volume, source, target, raylen, labels)  # keeps the raw pointers alive
             ctx.mode = "recompute"
-        if ctx.needs_input_grad[0]:
-            raise _lib.XvrB200Error("d/dvolume of the trilinear renderer is not available yet")
         return out
 
     @staticmethod
     def backward(ctx, gout):
-        C, n_points, step_mode, eps, det_h, det_w, lw, cw = ctx.cfg
         gout = cuda_f32(gout, "grad_output")
         B, _, N = gout.shape
         dev = gout.device
@@ -98,18 +152,14 @@ class _TrilinearRays(torch.autograd.Function):
         gtarget = torch.empty(B, N, 3, device=dev, dtype=torch.float32)
         graylen = torch.empty(B, 1, N, device=dev, dtype=torch.float32)
         work = torch.empty(B, 3, N, device=dev, dtype=torch.float32)
-        gvol = None
         if ctx.mode == "jac":
             (jac,) = ctx.saved_tensors
             call("xvr_rays_jac_bwd", ptr(jac), ptr(gout), B, N, ptr(gsource), ptr(gtarget), ptr(graylen),
                  ptr(work), stream())
         else:
-            volume, source, target, raylen, labels = ctx.saved_tensors
-            D0, D1, D2 = volume.shape
-            call("xvr_trilinear_rays_bwd", ptr(volume), D0, D1, D2, ptr(labels), C, ptr(source), ptr(target),
-                 ptr(raylen), B, N, n_points, step_mode, eps, det_h, det_w, lw, cw, ptr(gout), ptr(gsource),
-                 ptr(gtarget), ptr(graylen), ptr(work), stream())
-        return gvol, gsource, gtarget, graylen, None, None, None, None, None, None
+            call(f"xvr_{ctx.kind}_rays_bwd", *ctx.common, ptr(gout), ptr(gsource), ptr(gtarget), ptr(graylen),
+                 ptr(work), stream())
+        return None, gsource, gtarget, graylen, None, None, None, None, None, None
 
 
 class Trilinear(torch.nn.Module):
@@ -126,6 +176,7 @@ class Trilinear(torch.nn.Module):
         self.step = step
         self.detector_hw = None  # set by DRR so that warps map to compact detector tiles
         self._labels = _LabelCache()
+        self._texture = _VolumeTexture()
 
     def dims(self, volume):
         return torch.tensor(volume.shape).to(volume) - 1
@@ -135,8 +186,10 @@ class Trilinear(torch.nn.Module):
         if not align_corners:
             raise NotImplementedError("xvr_b200.Trilinear implements align_corners=True (the DiffDRR default)")
         labels, C = (None, 1) if mask is None else self._labels.get(mask)
-        return _TrilinearRays.apply(volume, source, target, img, labels, C, int(n_points),
-                                    conv.STEP_MODES[self.step], float(self.eps), self.detector_hw)
+        volume = cuda_f32(volume, "volume")
+        return _RenderRays.apply(volume, source, target, img, labels, C, "trilinear",
+                                 (int(n_points), conv.STEP_MODES[self.step], float(self.eps)), self.detector_hw,
+                                 self._texture.get(volume))
 
 
 class Siddon(torch.nn.Module):
@@ -159,8 +212,6 @@ class Siddon(torch.nn.Module):
         return torch.tensor(volume.shape).to(volume) + 1
 
     def forward(self, volume, source, target, img, mask=None):
-        from ._siddon import siddon_rays  # noqa: PLC0415  (kept separate: its library half is built -fmad=false)
-
         labels, C = (None, 1) if mask is None else self._labels.get(mask)
-        return siddon_rays(volume, source, target, img, labels, C, float(self.voxel_shift), float(self.eps),
-                           self.detector_hw)
+        return _RenderRays.apply(cuda_f32(volume, "volume"), source, target, img, labels, C, "siddon",
+                                 (float(self.voxel_shift), float(self.eps)), self.detector_hw, False)
