@@ -287,7 +287,7 @@ def main():
         total = world * B * args.steps
         value = total / (ms * 1e-3)
         peak, peak_src = peaks()
-        name = "xvr_trilinear_rays_fwd"
+        name = "xvr_trilinear_drr_fwd" if "xvr_trilinear_drr_fwd" in kernel_ms else "xvr_trilinear_rays_fwd"
         k_ms = kernel_ms.get(name, [])
         k_avg = sum(k_ms) / len(k_ms) if k_ms else float("nan")
         alg = B * algorithmic_bytes_fwd(H, W, N_POINTS)

@@ -147,6 +147,54 @@ def test_jacobian_and_recompute_backward_agree(cuda):
     assert rel_l2(gt, t.grad) < 1e-5
 
 
+def test_fused_and_generic_paths_agree(cuda, monkeypatch):
+    """DRR.forward's fused kernel (in-kernel ray generation, dL/dG reduction) against the materialised
+    detector -> affine_inverse -> renderer sequence of trainer.py:283-289."""
+    drr = make_drr(96, 40, width=56)
+    rot, xyz = pose_params(3, seed=12)
+    wimg = torch.rand(3, 1, 40, 56, device=cuda)
+    res = []
+    for fused in ("1", "0"):
+        monkeypatch.setenv("XVR_B200_FUSED", fused)
+        r, x = rot.clone().requires_grad_(), xyz.clone().requires_grad_()
+        img = _render(drr, r, x)
+        (img * wimg).sum().backward()
+        res.append((img.detach(), r.grad, x.grad))
+    assert rel_l2(res[0][0], res[1][0]) < 2e-5
+    # the noisy phantom's gradient is a heavily cancelling sum of piecewise-constant voxel differences: moving
+    # the ray end points by one fp32 ulp changes it at the 1e-3 level (the smooth-volume test below is tight)
+    assert rel_l2(res[0][1], res[1][1]) < 5e-3
+    assert rel_l2(res[0][2], res[1][2]) < 5e-3
+
+
+def _smooth_drr(cuda, n=64, h=32, renderer="trilinear"):
+    from xvr_b200.data import read
+
+    ax = torch.linspace(-1, 1, n)
+    X, Y, Z = torch.meshgrid(ax, ax, ax, indexing="ij")
+    vol = 800 * torch.exp(-((X - 0.1) ** 2 + (Y + 0.2) ** 2 + Z**2) / 0.18) + 400 * torch.exp(
+        -((X + 0.3) ** 2 + (Y - 0.1) ** 2 + (Z - 0.2) ** 2) / 0.08) - 700
+    import numpy as np
+
+    sub = read(vol, affine=np.diag([256.0 / n] * 3 + [1.0]))
+    return xvr_b200.DRR(sub, 1020.0, h, 1.08821875 * 256 / h, renderer=renderer, reverse_x_axis=False).to(cuda)
+
+
+@pytest.mark.parametrize("fused", ["1", "0"])
+def test_pose_gradients_smooth_volume_tight(cuda, monkeypatch, fused):
+    """On a smooth volume the analytic Jacobian must match autograd through grid_sample to 2e-4."""
+    monkeypatch.setenv("XVR_B200_FUSED", fused)
+    drr = _smooth_drr(cuda)
+    rot, xyz = pose_params(3, seed=13)
+    wimg = torch.rand(3, 1, 32, 32, device=cuda)
+    r1, x1 = rot.clone().requires_grad_(), xyz.clone().requires_grad_()
+    (_render(drr, r1, x1) * wimg).sum().backward()
+    r2, x2 = rot.clone().requires_grad_(), xyz.clone().requires_grad_()
+    (oracle_render(drr, r2, x2) * wimg).sum().backward()
+    assert rel_l2(r1.grad, r2.grad) < 2e-4
+    assert rel_l2(x1.grad, x2.grad) < 2e-4
+
+
 def test_texture_and_linear_gathers_agree_bitwise(cuda, monkeypatch):
     """The TLD4 path fetches the same fp32 texels as the scalar-load path: images and gradients are identical."""
     drr = make_drr(64, 32)
@@ -158,8 +206,9 @@ def test_texture_and_linear_gathers_agree_bitwise(cuda, monkeypatch):
         img = _render(drr, r, x)
         img.sum().backward()
         res.append((img.detach(), r.grad, x.grad))
-    for a, b in zip(*res):
-        assert torch.equal(a, b)
+    for other in res[1:]:
+        for a, b in zip(res[0], other):
+            assert torch.equal(a, b)
 
 
 def test_texture_tracks_volume_updates(cuda):
@@ -169,7 +218,7 @@ def test_texture_tracks_volume_updates(cuda):
     img0 = _render(drr, rot, xyz)
     drr.density.mul_(2.0)
     img1 = _render(drr, rot, xyz)
-    assert rel_l2(img1, 2 * img0) < 1e-6
+    assert rel_l2(img1, 2 * img0) < 1e-5
     pose = xvr_b200.convert(rot, xyz, parameterization="euler_angles", convention="ZXY")
     source, target = drr.detector(pose, None)
     raylen = (target - source).norm(dim=-1).unsqueeze(1)
@@ -177,7 +226,7 @@ def test_texture_tracks_volume_updates(cuda):
     for scale in (3.0, 5.0):
         tmp = drr.density * scale  # fresh tensor every step, possibly at a recycled address
         img = drr.renderer(tmp, source, target, raylen).view_as(img1)
-        assert rel_l2(img, scale * img1) < 1e-6
+        assert rel_l2(img, scale * img1) < 1e-5
         del tmp
 
 

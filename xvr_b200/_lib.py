@@ -27,6 +27,10 @@ _SIGNATURES = {
     "xvr_trilinear_rays_bwd": (
         [P, P, c_int, c_int, c_int, P, c_int, P, P, P, c_int, c_int, c_int, c_int, c_float, c_int, c_int, c_int,
          c_int, P, P, P, P, P, P], c_int),
+    "xvr_trilinear_drr_fwd": (
+        [P, P, c_int, c_int, c_int, P, P, ctypes.POINTER(c_float), c_int, c_int, c_int, c_int, c_int, c_float, c_int,
+         c_int, P, P, P], c_int),
+    "xvr_drr_jac_bwd": ([P, P, ctypes.POINTER(c_float), c_int, c_int, c_int, P, P], c_int),
     "xvr_rays_jac_bwd": ([P, P, c_int, c_int, P, P, P, P, P], c_int),
     "xvr_reduce_rows": ([P, c_int, c_int, P, P], c_int),
     "xvr_siddon_rays_fwd": (

@@ -42,6 +42,40 @@ __device__ __forceinline__ float4 gather_yz(cudaTextureObject_t tex, int layer, 
   return r;
 }
 
+// In-kernel ray generation (the fused DRR path): the detector point of pixel (i, j) in the camera frame is
+// c = o + i*u + j*v; its voxel-space target is G c, the source is G's translation column and the world-mm ray
+// length is |M_rot c| (DiffDRR detector.py + drr.py as sequenced at /root/reference/src/xvr/model/trainer.py:283-285).
+struct DetectorGeom {
+  const float* __restrict__ cam2vox;    // (B,3,4) row-major, camera -> voxel-index coordinates
+  const float* __restrict__ cam2world;  // (B,3,4) row-major, camera -> world mm (rotation part gives the length)
+  float o[3], u[3], v[3];
+  int W;
+};
+
+__device__ __forceinline__ void camera_point(const DetectorGeom& g, int n, float c[3]) {
+  const int i = n / g.W, j = n - i * g.W;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) c[a] = fmaf((float)j, g.v[a], fmaf((float)i, g.u[a], g.o[a]));
+}
+
+// source s, direction d = t - s + eps (voxel coords) and world ray length L of ray n of pose b
+__device__ __forceinline__ void generate_ray(const DetectorGeom& g, int b, int n, float eps, float s[3], float d[3],
+                                             float& L) {
+  float c[3];
+  camera_point(g, n, c);
+  const float* G = g.cam2vox + b * 12;
+  const float* M = g.cam2world + b * 12;
+  float w[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    s[a] = __ldg(G + a * 4 + 3);
+    const float t = fmaf(__ldg(G + a * 4 + 2), c[2], fmaf(__ldg(G + a * 4 + 1), c[1], fmaf(__ldg(G + a * 4), c[0], s[a])));
+    d[a] = (t - s[a]) + eps;
+    w[a] = fmaf(__ldg(M + a * 4 + 2), c[2], fmaf(__ldg(M + a * 4 + 1), c[1], __ldg(M + a * 4) * c[0]));
+  }
+  L = sqrtf(fmaf(w[0], w[0], fmaf(w[1], w[1], w[2] * w[2])));
+}
+
 // Slab test of the segment s + alpha*d, alpha in [0,1], against the box [lo, hi]^3 (per axis).
 // Restates DiffDRR renderers._get_alpha_minmax: per-axis (plane - s)/d with IEEE division, min/max over the
 // two planes, max/min over axes, then the clamp to [0,1].  Also reports which plane is active for the
@@ -97,8 +131,8 @@ __device__ __forceinline__ float sample_trilinear(const Vol& v, float x, float y
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
     const float tu = fz0 + 1.0f, tv = fy0 + 1.0f;
     if ((unsigned)ix < (unsigned)v.D0) a = gather_yz(v.tex, ix, tu, tv);
-    if ((unsigned)(ix + 1) < (unsigned)v.D0) b = gather_yz(v.tex, ix + 1, tu, tv);
     c010 = a.x; c011 = a.y; c001 = a.z; c000 = a.w;
+    if ((unsigned)(ix + 1) < (unsigned)v.D0) b = gather_yz(v.tex, ix + 1, tu, tv);
     c110 = b.x; c111 = b.y; c101 = b.z; c100 = b.w;
   } else if ((unsigned)ix < (unsigned)(v.D0 - 1) && (unsigned)iy < (unsigned)(v.D1 - 1) &&
       (unsigned)iz < (unsigned)(v.D2 - 1)) {

@@ -16,6 +16,8 @@ struct TrilinearParams {
   const float* __restrict__ source;    // (B,1,3) voxel coords
   const float* __restrict__ target;    // (B,N,3)
   const float* __restrict__ raylen;    // (B,N) world-mm ray length (trainer.py:284)
+  bool fused;                          // rays generated in-kernel from `geom` instead of source/target/raylen
+  DetectorGeom geom;
   int B, N;
   int n_points;
   int step_mode;  // 0: span/(n-1)   1: span/n   2: 1/n
@@ -66,13 +68,17 @@ __global__ void __launch_bounds__(256) trilinear_fwd_kernel(const TrilinearParam
   if (n < 0) return;
   const int64_t ray = (int64_t)b * p.N + n;
 
-  float s[3], d[3];
+  float s[3], d[3], L;
+  if (p.fused) {
+    generate_ray(p.geom, b, n, p.eps, s, d, L);
+  } else {
 #pragma unroll
-  for (int a = 0; a < 3; ++a) {
-    s[a] = __ldg(p.source + b * 3 + a);
-    d[a] = (__ldg(p.target + ray * 3 + a) - s[a]) + p.eps;
+    for (int a = 0; a < 3; ++a) {
+      s[a] = __ldg(p.source + b * 3 + a);
+      d[a] = (__ldg(p.target + ray * 3 + a) - s[a]) + p.eps;
+    }
+    L = __ldg(p.raylen + ray);
   }
-  const float L = __ldg(p.raylen + ray);
   const int np = p.n_points;
 
   float lo[3] = {0.f, 0.f, 0.f};
@@ -173,13 +179,17 @@ __global__ void __launch_bounds__(256) trilinear_bwd_kernel(const TrilinearParam
   if (n < 0) return;
   const int64_t ray = (int64_t)b * p.N + n;
 
-  float s[3], d[3];
+  float s[3], d[3], L;
+  if (p.fused) {
+    generate_ray(p.geom, b, n, p.eps, s, d, L);
+  } else {
 #pragma unroll
-  for (int a = 0; a < 3; ++a) {
-    s[a] = __ldg(p.source + b * 3 + a);
-    d[a] = (__ldg(p.target + ray * 3 + a) - s[a]) + p.eps;
+    for (int a = 0; a < 3; ++a) {
+      s[a] = __ldg(p.source + b * 3 + a);
+      d[a] = (__ldg(p.target + ray * 3 + a) - s[a]) + p.eps;
+    }
+    L = __ldg(p.raylen + ray);
   }
-  const float L = __ldg(p.raylen + ray);
   const int np = p.n_points;
   float g1 = 0.f;
   if (LABELS) {
@@ -287,6 +297,62 @@ __global__ void __launch_bounds__(1024) reduce_rows_kernel(const float* __restri
   }
 }
 
+// Fused-path backward: dL/dG (B,3,4) from the saved per-ray Jacobian.  t_r = G [c_r; 1], s = G[:,3]  =>
+// dL/dG[:, :3] = sum_r g_r J_t,r (x) c_r,  dL/dG[:, 3] = sum_r g_r (J_t,r + J_s,r).  One CTA per pose, fixed tree.
+__global__ void __launch_bounds__(1024)
+drr_jac_bwd_kernel(const float* __restrict__ jac, const float* __restrict__ gout, int N, DetectorGeom geom,
+                   float* __restrict__ gG) {
+  __shared__ float part[32][12];
+  const int b = blockIdx.x;
+  float acc[12];
+#pragma unroll
+  for (int k = 0; k < 12; ++k) acc[k] = 0.f;
+  const float* j = jac + (int64_t)b * 7 * N;
+  for (int n = threadIdx.x; n < N; n += 1024) {
+    const float g = __ldg(gout + (int64_t)b * N + n);
+    float c[3];
+    camera_point(geom, n, c);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const float gt = g * __ldg(j + (int64_t)(3 + a) * N + n);
+      const float gs = g * __ldg(j + (int64_t)a * N + n);
+      acc[a * 4 + 0] = fmaf(gt, c[0], acc[a * 4 + 0]);
+      acc[a * 4 + 1] = fmaf(gt, c[1], acc[a * 4 + 1]);
+      acc[a * 4 + 2] = fmaf(gt, c[2], acc[a * 4 + 2]);
+      acc[a * 4 + 3] += gt + gs;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 12; ++k) {
+    const float v = warp_sum(acc[k]);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+#pragma unroll
+    for (int k = 0; k < 12; ++k) {
+      const float v = warp_sum(part[threadIdx.x][k]);
+      if (threadIdx.x == 0) gG[b * 12 + k] = v;
+    }
+  }
+}
+
+static int fill_geom(DetectorGeom& g, const float* cam2vox, const float* cam2world, const float* det9, int W) {
+  if (!cam2vox || !cam2world || !det9 || W <= 0) {
+    set_last_error("xvr_drr: null geometry argument");
+    return XVR_ERR_INVALID;
+  }
+  g.cam2vox = cam2vox;
+  g.cam2world = cam2world;
+  for (int a = 0; a < 3; ++a) {
+    g.o[a] = det9[a];
+    g.u[a] = det9[3 + a];
+    g.v[a] = det9[6 + a];
+  }
+  g.W = W;
+  return XVR_OK;
+}
+
 static int fill_map(TileMap& m, int N, int det_h, int det_w, int lane_w_log2, int cta_w_log2, int* tiles) {
   if (det_w > 0 && det_h > 0) {
     if ((int64_t)det_h * det_w != N) {
@@ -323,7 +389,7 @@ static int fill_common(TrilinearParams& p, const float* volume, const void* volt
                        int C, const float* source, const float* target, const float* raylen, int B, int N,
                        int n_points, int step_mode, float eps, int det_h, int det_w, int lane_w_log2,
                        int cta_w_log2) {
-  if (!volume || !source || !target || !raylen || B <= 0 || N <= 0 || D0 < 2 || D1 < 2 || D2 < 2 ||
+  if (!volume || ((!source || !target || !raylen) && !p.fused) || B <= 0 || N <= 0 || D0 < 2 || D1 < 2 || D2 < 2 ||
       n_points < 2 || step_mode < 0 || step_mode > 2 || C < 1 || (labels && C > 255) || (!labels && C != 1)) {
     set_last_error("xvr_trilinear: invalid argument");
     return XVR_ERR_INVALID;
@@ -460,4 +526,54 @@ extern "C" int xvr_rays_jac_bwd(const float* jac, const float* gout, int B, int 
   if (rc) return rc;
   reduce_rows_kernel<<<B * 3, 1024, 0, st>>>(workspace, N, gsource);
   return check_launch("xvr_rays_jac_bwd/reduce");
+}
+
+// Fused DRR forward: rays are generated in-kernel from the per-pose camera->voxel matrix and the detector basis
+// (det9 = origin, row step, column step of the pixel grid in the camera frame; a HOST array of 9 floats).
+extern "C" int xvr_trilinear_drr_fwd(const float* volume, const void* voltex, int D0, int D1, int D2,
+                                     const float* cam2vox, const float* cam2world, const float* det9, int B,
+                                     int det_h, int det_w, int n_points, int step_mode, float eps, int lane_w_log2,
+                                     int cta_w_log2, float* out, float* jac, void* stream) {
+  TrilinearParams p = {};
+  p.fused = true;
+  int rc = fill_geom(p.geom, cam2vox, cam2world, det9, det_w);
+  if (rc) return rc;
+  rc = fill_common(p, volume, voltex, D0, D1, D2, nullptr, 1, nullptr, nullptr, nullptr, B, det_h * det_w, n_points,
+                   step_mode, eps, det_h, det_w, lane_w_log2, cta_w_log2);
+  if (rc) return rc;
+  if (!out) {
+    set_last_error("xvr_trilinear_drr_fwd: out is null");
+    return XVR_ERR_INVALID;
+  }
+  p.out = out;
+  p.jac = jac;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t grid = (int64_t)B * p.tiles_per_pose;
+  if (grid >= (int64_t)1 << 31) {
+    set_last_error("xvr_trilinear_drr_fwd: grid too large");
+    return XVR_ERR_INVALID;
+  }
+  const bool tex = p.vol.tex != 0;
+  if (jac) {
+    auto k = tex ? trilinear_fwd_kernel<true, false, true> : trilinear_fwd_kernel<true, false, false>;
+    k<<<(unsigned)grid, 256, 0, st>>>(p);
+  } else {
+    auto k = tex ? trilinear_fwd_kernel<false, false, true> : trilinear_fwd_kernel<false, false, false>;
+    k<<<(unsigned)grid, 256, 0, st>>>(p);
+  }
+  return check_launch("xvr_trilinear_drr_fwd");
+}
+
+// Backward of any fused DRR forward that saved its per-ray Jacobian: gG (B,3,4) = dL/d(cam2vox).
+extern "C" int xvr_drr_jac_bwd(const float* jac, const float* gout, const float* det9, int B, int det_h, int det_w,
+                               float* gG, void* stream) {
+  if (!jac || !gout || !gG || B <= 0 || det_h <= 0) {
+    set_last_error("xvr_drr_jac_bwd: invalid argument");
+    return XVR_ERR_INVALID;
+  }
+  DetectorGeom g = {};
+  int rc = fill_geom(g, jac, jac, det9, det_w);  // the matrices are not read by the reduction
+  if (rc) return rc;
+  drr_jac_bwd_kernel<<<B, 1024, 0, (cudaStream_t)stream>>>(jac, gout, det_h * det_w, g, gG);
+  return check_launch("xvr_drr_jac_bwd");
 }

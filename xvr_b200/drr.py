@@ -9,6 +9,8 @@ calls ``drr.detector(pose, None)``, ``drr.affine_inverse(points)``, ``drr.render
 ``perspective_projection`` / ``inverse_projection`` (/root/reference/src/xvr/metrics/evaluator.py:17-29).
 """
 
+import os
+
 import numpy as np
 import torch
 
@@ -159,11 +161,19 @@ class DRR(torch.nn.Module):
         if self.density is None:
             raise RuntimeError("drr.density was unloaded; call drr.renderer(volume, ...) directly "
                                "(as xvr's Trainer.render_samples does) or restore it")
+        mask = getattr(self, "mask", None) if mask_to_channels else None
+        if (mask is None and calibration is None and isinstance(self.renderer, Trilinear) and self.reshape
+                and os.environ.get("XVR_B200_FUSED", "1") == "1"):
+            # fused path: one kernel generates the rays, marches them and (if needed) emits the pose Jacobian
+            cam2world = self.detector.reorient.compose(pose).matrix
+            cam2vox = self._affine_inverse @ cam2world
+            img = self.renderer.render_drr(self.density, cam2vox[:, :3].contiguous(), cam2world[:, :3].contiguous(),
+                                           self.detector, **kwargs)
+            return self.reshape_transform(img, batch_size=len(pose))
         source, target = self.detector(pose, calibration)
         raylen = (target - source).norm(dim=-1).unsqueeze(1)
         source = self.affine_inverse(source)
         target = self.affine_inverse(target)
-        mask = getattr(self, "mask", None) if mask_to_channels else None
         img = self.renderer(self.density, source, target, raylen, mask=mask, **kwargs)
         return self.reshape_transform(img, batch_size=len(pose))
 

@@ -42,7 +42,8 @@ class _VolumeTexture:
         self.version = None
 
     def get(self, volume):
-        if os.environ.get("XVR_B200_GATHER", "tex") != "tex":
+        mode = os.environ.get("XVR_B200_GATHER", "tex")
+        if mode == "ldg":
             return None
         shape = tuple(volume.shape)
         if self.handle is None or shape != self.shape or volume.device != self.device:
@@ -162,6 +163,36 @@ class _RenderRays(torch.autograd.Function):
         return None, gsource, gtarget, graylen, None, None, None, None, None, None
 
 
+class _RenderDRR(torch.autograd.Function):
+    """Fused DRR: rays are generated inside the kernel from cam2vox (B,3,4) and the detector basis, so no
+    (B,N,3) tensor exists; the backward reduces the saved per-ray Jacobian straight to dL/dcam2vox (B,3,4)."""
+
+    @staticmethod
+    def forward(ctx, volume, cam2vox, cam2world, det9, det_hw, args, voltex):
+        cam2vox, cam2world = cuda_f32(cam2vox, "cam2vox"), cuda_f32(cam2world, "cam2world")
+        B = cam2vox.shape[0]
+        H, W = det_hw
+        lw, cw = _tile_shape()
+        out = torch.empty(B, 1, H * W, device=volume.device, dtype=torch.float32)
+        jac = torch.empty(B, 7, H * W, device=volume.device, dtype=torch.float32) if ctx.needs_input_grad[1] else None
+        det = (ctypes.c_float * 9)(*det9)
+        call("xvr_trilinear_drr_fwd", ptr(volume), voltex, *volume.shape, ptr(cam2vox), ptr(cam2world), det, B, H, W,
+             *args, lw, cw, ptr(out), ptr(jac), stream())
+        if jac is not None:
+            ctx.save_for_backward(jac)
+            ctx.det = (det, B, H, W)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        (jac,) = ctx.saved_tensors
+        det, B, H, W = ctx.det
+        gout = cuda_f32(gout, "grad_output")
+        gG = torch.empty(B, 3, 4, device=gout.device, dtype=torch.float32)
+        call("xvr_drr_jac_bwd", ptr(jac), ptr(gout), det, B, H, W, ptr(gG), stream())
+        return None, gG, None, None, None, None, None
+
+
 class Trilinear(torch.nn.Module):
     """Trilinear ray-marching renderer (``diffdrr.renderers.Trilinear``), n_points samples per ray."""
 
@@ -190,6 +221,17 @@ class Trilinear(torch.nn.Module):
         return _RenderRays.apply(volume, source, target, img, labels, C, "trilinear",
                                  (int(n_points), conv.STEP_MODES[self.step], float(self.eps)), self.detector_hw,
                                  self._texture.get(volume))
+
+
+    def render_drr(self, volume, cam2vox, cam2world, detector, n_points=conv.TRILINEAR_N_POINTS):
+        """Fused path used by ``DRR.forward``: ``cam2vox``/``cam2world`` are (B,3,4) camera->voxel / camera->world
+        matrices, ``detector`` supplies the pixel grid.  Returns (B,1,H*W)."""
+        volume = cuda_f32(volume, "volume")
+        origin, row_step, col_step = detector.pixel_basis()
+        return _RenderDRR.apply(volume, cam2vox, cam2world, (*origin, *row_step, *col_step),
+                                (detector.height, detector.width),
+                                (int(n_points), conv.STEP_MODES[self.step], float(self.eps)),
+                                self._texture.get(volume))
 
 
 class Siddon(torch.nn.Module):
