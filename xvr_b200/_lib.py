@@ -32,6 +32,10 @@ _SIGNATURES = {
          c_int, P, P, P], c_int),
     "xvr_drr_jac_bwd": ([P, P, ctypes.POINTER(c_float), c_int, c_int, c_int, P, P], c_int),
     "xvr_rays_jac_bwd": ([P, P, c_int, c_int, P, P, P, P, P], c_int),
+    "xvr_ncc_fwd": ([P, P, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_int, P, P, P, P, P], c_int),
+    "xvr_ncc_bwd": ([P, P, P, c_int, P, c_int, c_int, c_int, c_int, c_int, c_float, c_int, P, P], c_int),
+    "xvr_sobel_fwd": ([P, c_int, c_int, c_int, P, P], c_int),
+    "xvr_sobel_bwd": ([P, c_int, c_int, c_int, P, P], c_int),
     "xvr_reduce_rows": ([P, c_int, c_int, P, P], c_int),
     "xvr_siddon_rays_fwd": (
         [P, c_int, c_int, c_int, P, c_int, P, P, P, c_int, c_int, c_float, c_float, c_int, c_int, c_int, c_int, P, P,
