@@ -1,0 +1,104 @@
+/* xvr_b200 -- C-ABI of libxvr_b200.so: hand-written sm_100a kernels for xvr's DRR hot path.
+ *
+ * The reference (eigenvivek/xvr) has no FFI: its hot path is the Python API of the un-vendored dependency
+ * diffdrr==0.6.0 (/root/reference/pyproject.toml:14).  Each entry point below names the DiffDRR symbol it
+ * replaces and the xvr call site that pins its interface.  Conventions:
+ *   - every pointer is a DEVICE pointer to contiguous fp32 (uint8 for label volumes) unless marked HOST;
+ *   - the caller owns all buffers; nothing is allocated except by xvr_volume_create;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream); all work is asynchronous on it and
+ *     graph-capturable;
+ *   - return value 0 = OK, -1 = invalid argument, -2 = CUDA error; xvr_last_error() gives the message
+ *     (thread-local).  Nothing aborts, nothing falls back to the CPU.
+ *   - volume[D0][D1][D2] with D2 contiguous; ray end points are in voxel-index coordinates of that array
+ *     (what drr.affine_inverse(...) returns at /root/reference/src/xvr/model/trainer.py:285).
+ */
+#ifndef XVR_B200_H
+#define XVR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+int xvr_abi_version(void);
+const char* xvr_last_error(void);
+/* kernels launched by this library since it was loaded */
+long long xvr_launch_count(void);
+
+/* ---- Volume texture: a block-linear (layered cudaArray) copy of the CT volume for the TLD4 corner gathers.
+ * Replaces nothing in the reference (which samples with F.grid_sample on the linear tensor); it is the HBM layout
+ * the trilinear kernels prefer.  Optional: pass NULL as `voltex` below to gather from the linear volume. */
+int xvr_volume_create(int D0, int D1, int D2, void** handle_out);
+int xvr_volume_upload(void* handle, const float* volume, void* stream);
+int xvr_volume_destroy(void* handle);
+
+/* ---- Trilinear renderer = diffdrr.renderers.Trilinear.forward
+ * call site /root/reference/src/xvr/model/trainer.py:288  drr.renderer(vol, source, target, raylen, mask=seg)
+ *   source (B,1,3), target (B,N,3), raylen (B,N); labels (D0,D1,D2) uint8 or NULL with C = max label + 1 (else 1)
+ *   step_mode 0: span/(n-1)  1: span/n  2: 1/n ;  det_h*det_w == N selects compact detector tiles (0,0 = linear)
+ *   out (B,C,N);  jac (B,7,N) or NULL: per-ray d out/d(source xyz, target xyz, raylen) (only without labels) */
+int xvr_trilinear_rays_fwd(const float* volume, const void* voltex, int D0, int D1, int D2, const uint8_t* labels,
+                           int C, const float* source, const float* target, const float* raylen, int B, int N,
+                           int n_points, int step_mode, float eps, int det_h, int det_w, int lane_w_log2,
+                           int cta_w_log2, float* out, float* jac, void* stream);
+/* autograd backward of the above (= grid_sample backward + glue): re-marches the rays.
+ *   gout (B,C,N) -> gsource (B,1,3), gtarget (B,N,3), graylen (B,N); workspace (B,3,N) */
+int xvr_trilinear_rays_bwd(const float* volume, const void* voltex, int D0, int D1, int D2, const uint8_t* labels,
+                           int C, const float* source, const float* target, const float* raylen, int B, int N,
+                           int n_points, int step_mode, float eps, int det_h, int det_w, int lane_w_log2,
+                           int cta_w_log2, const float* gout, float* gsource, float* gtarget, float* graylen,
+                           float* workspace, void* stream);
+/* backward through a Jacobian saved by a *_rays_fwd call: 28 bytes per ray instead of a second march */
+int xvr_rays_jac_bwd(const float* jac, const float* gout, int B, int N, float* gsource, float* gtarget,
+                     float* graylen, float* workspace, void* stream);
+
+/* ---- Fused DRR = diffdrr.drr.DRR.forward (detector -> ray length -> affine_inverse -> Trilinear -> reshape),
+ * the sequence xvr restates at /root/reference/src/xvr/model/trainer.py:283-289 and reaches through
+ * Registration.forward at /root/reference/src/xvr/registrar/base.py:249.
+ *   cam2vox, cam2world (B,3,4) row-major; det9 HOST float[9] = detector origin, row step, column step (camera mm)
+ *   out (B,1,H*W); jac (B,7,H*W) or NULL */
+int xvr_trilinear_drr_fwd(const float* volume, const void* voltex, int D0, int D1, int D2, const float* cam2vox,
+                          const float* cam2world, const float* det9, int B, int det_h, int det_w, int n_points,
+                          int step_mode, float eps, int lane_w_log2, int cta_w_log2, float* out, float* jac,
+                          void* stream);
+/* gG (B,3,4) = dL/d cam2vox from the saved Jacobian and gout (B,1,H*W) */
+int xvr_drr_jac_bwd(const float* jac, const float* gout, const float* det9, int B, int det_h, int det_w, float* gG,
+                    void* stream);
+
+/* ---- Siddon renderer = diffdrr.renderers.Siddon.forward (same call sites, --renderer siddon)
+ * Traversed voxel indices are bit-identical to the reference's sort + grid_sample(nearest) formulation. */
+int xvr_siddon_rays_fwd(const float* volume, int D0, int D1, int D2, const uint8_t* labels, int C,
+                        const float* source, const float* target, const float* raylen, int B, int N,
+                        float voxel_shift, float eps, int det_h, int det_w, int lane_w_log2, int cta_w_log2,
+                        float* out, float* jac, void* stream);
+int xvr_siddon_rays_bwd(const float* volume, int D0, int D1, int D2, const uint8_t* labels, int C,
+                        const float* source, const float* target, const float* raylen, int B, int N,
+                        float voxel_shift, float eps, int det_h, int det_w, int lane_w_log2, int cta_w_log2,
+                        const float* gout, float* gsource, float* gtarget, float* graylen, float* workspace,
+                        void* stream);
+/* test hook: the traversal itself. idx/seg (B,N,trace_max), count (B,N) */
+int xvr_siddon_trace(const float* volume, int D0, int D1, int D2, const float* source, const float* target, int B,
+                     int N, float voxel_shift, float eps, int trace_max, int32_t* idx, float* seg, int32_t* count,
+                     void* stream);
+
+/* ---- Similarity = diffdrr.metrics.{NormalizedCrossCorrelation2d, MultiscaleNormalizedCrossCorrelation2d,
+ * GradientNormalizedCrossCorrelation2d, Sobel}; call sites /root/reference/src/xvr/model/loss.py:16,27 and
+ * /root/reference/src/xvr/registrar/base.py:119-122.
+ *   x1, x2 (B,C,H,W); patch <= 0 = whole-image NCC; score (B,) (+)= weight * NCC
+ *   workspace >= B*C*max(6, ceil(H/16)*ceil(W/16)) floats
+ *   coef2 / coef1: NULL or (B*C,4,H-p+1,W-p+1) [(B*C,6) when patch <= 0], consumed by xvr_ncc_bwd for d/dx2, d/dx1 */
+int xvr_ncc_fwd(const float* x1, const float* x2, int B, int C, int H, int W, int patch, float eps, float weight,
+                int accumulate, float* score, float* workspace, float* coef2, float* coef1, void* stream);
+int xvr_ncc_bwd(const float* x1, const float* x2, const float* coef, int which, const float* gscore, int B, int C,
+                int H, int W, int patch, float weight, int accumulate, float* grad, void* stream);
+int xvr_sobel_fwd(const float* x, int B, int H, int W, float* out /* (B,2,H,W) */, void* stream);
+int xvr_sobel_bwd(const float* gout, int B, int H, int W, float* gx /* (B,1,H,W) */, void* stream);
+
+/* out[r] = sum_n in[r,n], fixed summation tree */
+int xvr_reduce_rows(const float* in, int rows, int N, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

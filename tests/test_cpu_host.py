@@ -1,0 +1,233 @@
+"""CPU suite, part 2: host-side logic of xvr_b200 (no kernels are launched) against the oracle, the C-ABI
+export table, and the mirrored conventions."""
+
+import copy
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+import xvr_b200
+from oracle import knobs
+from xvr_b200 import _conventions as conv
+from xvr_b200 import _lib
+from xvr_b200.data import read, synthetic_ct, transform_hu_to_density
+from xvr_b200.preprocess import XrayTransforms
+from xvr_b200.sampler import get_random_pose
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = torch.load(os.path.join(os.path.dirname(__file__), "golden", "oracle_v1.pt"), weights_only=False)
+
+
+# ------------------------------------------------------------------------------------------------ C-ABI
+def _header_prototypes():
+    text = open(os.path.join(ROOT, "include", "xvr_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"\b(xvr_\w+)\s*\(([^;]*?)\)\s*;", text, flags=re.S):
+        args = m.group(2).strip()
+        protos[m.group(1)] = 0 if args in ("", "void") else args.count(",") + 1
+    return protos
+
+
+def test_library_exports_every_declared_symbol():
+    if not _lib.LIB.exists():
+        pytest.fail(f"{_lib.LIB} is missing: run __graft_entry__.build()")
+    handle = ctypes.CDLL(str(_lib.LIB))
+    protos = _header_prototypes()
+    assert len(protos) >= 19
+    for name in protos:
+        assert hasattr(handle, name), f"{name} declared in include/xvr_b200.h but not exported"
+    assert handle.xvr_abi_version() == 1
+
+
+def test_bindings_match_header_arity():
+    protos = _header_prototypes()
+    assert set(protos) == set(_lib.exported_symbols())
+    for name, (argtypes, _) in _lib._SIGNATURES.items():
+        assert len(argtypes) == protos[name], name
+
+
+def test_invalid_arguments_return_error_codes_not_crashes():
+    lib = _lib.lib()
+    assert lib.xvr_reduce_rows(None, 1, 1, None, None) == -1
+    assert b"xvr_reduce_rows" in lib.xvr_last_error()
+    assert lib.xvr_ncc_fwd(None, None, 1, 1, 8, 8, 0, 1e-5, 1.0, 0, None, None, None, None, None) == -1
+    assert lib.xvr_volume_create(0, 4, 4, ctypes.byref(ctypes.c_void_p())) == -1
+
+
+def test_product_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "xvr_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f"{f} imports oracle"
+
+
+def test_conventions_mirror_oracle_knobs():
+    pairs = {
+        "COMPOSE_APPLIES_SELF_FIRST": "COMPOSE_APPLIES_SELF_FIRST", "DET_SIGN_S": "DET_SIGN_S", "DET_SIGN_T": "DET_SIGN_T",
+        "TRILINEAR_N_POINTS": "TRILINEAR_N_POINTS", "TRILINEAR_STEP": "TRILINEAR_STEP", "RENDER_EPS": "RENDER_EPS",
+        "SIDDON_VOXEL_SHIFT_DEFAULT": "SIDDON_VOXEL_SHIFT_DEFAULT", "HU_AIR": "HU_AIR", "HU_BONE": "HU_BONE",
+        "NCC_EPS": "NCC_EPS", "GEODESIC_EPS": "GEODESIC_EPS",
+        "CONVERT_TRANSLATION_IN_ROTATED_FRAME": "CONVERT_TRANSLATION_IN_ROTATED_FRAME",
+    }
+    for a, b in pairs.items():
+        assert getattr(conv, a) == getattr(knobs, b), a
+
+
+# ------------------------------------------------------------------------------------------------ pose
+@pytest.mark.parametrize("name", list(xvr_b200.N_ANGULAR_COMPONENTS))
+def test_convert_matches_oracle_and_golden(name):
+    p = GOLD["poses"][name]
+    convention = "ZXY" if name == "euler_angles" else None
+    T = xvr_b200.convert(p["rot"], p["xyz"], parameterization=name, convention=convention)
+    assert torch.allclose(T.matrix, p["matrix"], atol=1e-5)
+    R = T.matrix[:, :3, :3]
+    assert torch.allclose(R @ R.transpose(-1, -2), torch.eye(3).expand(4, 3, 3), atol=1e-5)
+    # convert -> RigidTransform.convert -> convert is the identity on matrices
+    rot, xyz = T.convert(name, convention)
+    T2 = xvr_b200.convert(rot, xyz, parameterization=name, convention=convention)
+    assert torch.allclose(T2.matrix, T.matrix, atol=1e-4)
+
+
+def test_rigid_transform_algebra():
+    g = torch.Generator().manual_seed(0)
+    A = xvr_b200.convert(torch.randn(5, 3, generator=g), torch.randn(5, 3, generator=g) * 100,
+                         parameterization="euler_angles", convention="ZXY")
+    Bt = xvr_b200.convert(torch.randn(1, 3, generator=g), torch.randn(1, 3, generator=g) * 100,
+                          parameterization="axis_angle")
+    pts = torch.randn(5, 7, 3, generator=g)
+    assert torch.allclose(A.compose(Bt)(pts), Bt(A(pts)), atol=1e-3)  # A first, then B; batch of 1 broadcasts
+    assert torch.allclose(A.inverse()(A(pts)), pts, atol=1e-3)
+    assert torch.allclose((A @ A.inverse()).matrix, torch.eye(4).expand(5, 4, 4), atol=1e-4)
+    assert len(A) == 5 and len(A[torch.tensor([True, False, True, False, False])]) == 2
+    assert torch.equal(A[1:3].matrix, A.matrix[1:3])
+    assert torch.allclose(A.compose(Bt).matrix, oracle.compose(A.matrix, Bt.matrix))
+    assert torch.allclose(A.inverse().matrix, oracle.invert(A.matrix), atol=1e-5)
+
+
+def test_degrees_and_sampler():
+    torch.manual_seed(0)
+    pose = get_random_pose(-45, 45, -45, 45, -15, 15, -50, 50, 700, 900, -50, 50, 16)
+    rot, xyz = pose.convert("euler_angles", "ZXY", degrees=True)
+    assert rot[:, :2].abs().max() <= 45 + 1e-3 and rot[:, 2].abs().max() <= 15 + 1e-3
+    assert (xyz[:, 1] >= 700 - 1e-2).all() and (xyz[:, 1] <= 900 + 1e-2).all()
+    # the camera orbits the isocenter: |source| == |xyz|
+    assert torch.allclose(pose.matrix[:, :3, 3].norm(dim=-1), xyz.norm(dim=-1), rtol=1e-5)
+
+
+def test_geodesic_against_oracle():
+    from xvr_b200.metrics import DoubleGeodesicSE3
+
+    g = torch.Generator().manual_seed(2)
+    A = xvr_b200.convert(torch.randn(6, 3, generator=g) * 0.5, torch.randn(6, 3, generator=g) * 30,
+                         parameterization="euler_angles", convention="ZXY")
+    B = xvr_b200.convert(torch.randn(6, 3, generator=g) * 0.5, torch.randn(6, 3, generator=g) * 30,
+                         parameterization="euler_angles", convention="ZXY")
+    for a, b in zip(DoubleGeodesicSE3(1020.0)(A, B), oracle.double_geodesic(A.matrix, B.matrix, 1020.0)):
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-4)
+
+
+# ------------------------------------------------------------------------------------------------ DRR module
+def _drr(renderer="trilinear", **kw):
+    sub = read(GOLD["hu"], GOLD["labels"], affine=GOLD["affine"].numpy(), center_volume=False)
+    d = GOLD["detector"]
+    return xvr_b200.DRR(sub, d["sdd"], d["height"], d["delx"], d["width"], d["dely"], d["x0"], d["y0"],
+                        reverse_x_axis=d["reverse_x_axis"], renderer=renderer, **kw)
+
+
+def test_detector_matches_oracle():
+    drr = _drr()
+    d = GOLD["detector"]
+    pose = xvr_b200.convert(GOLD["rot"], GOLD["xyz"], parameterization="euler_angles", convention="ZXY")
+    src, tgt = drr.detector(pose, None)
+    osrc, otgt = oracle.detector_rays(pose.matrix, oracle.REORIENT["AP"], d["height"], d["width"], d["delx"],
+                                      d["dely"], d["x0"], d["y0"], d["sdd"], d["reverse_x_axis"])
+    assert torch.allclose(src, osrc, atol=1e-4) and torch.allclose(tgt, otgt, atol=1e-3)
+    # the in-kernel pixel basis reproduces the materialised grid
+    o, u, v = (torch.tensor(t) for t in drr.detector.pixel_basis())
+    i, j = torch.meshgrid(torch.arange(d["height"]), torch.arange(d["width"]), indexing="ij")
+    grid = o + i[..., None] * u + j[..., None] * v
+    assert torch.allclose(grid.reshape(1, -1, 3), drr.detector.target, atol=1e-4)
+    assert torch.equal(drr.density, GOLD["density"])
+
+
+def test_drr_surface_used_by_xvr():
+    drr = _drr("siddon", voxel_shift=0.0)
+    assert drr.renderer.voxel_shift == 0.0
+    assert isinstance(copy.deepcopy(drr), xvr_b200.DRR)
+    drr.set_intrinsics_(sdd=900.0, height=40, width=30, delx=2.0, dely=2.5, x0=-1.0, y0=2.0)
+    assert (drr.detector.height, drr.detector.width, drr.detector.sdd) == (40, 30, 900.0)
+    assert drr.detector.target.shape == (1, 1200, 3) and drr.renderer.detector_hw == (40, 30)
+    drr.rescale_detector_(0.25)
+    assert (drr.detector.height, drr.detector.width) == (10, 7) and drr.detector.delx == 8.0
+    img = torch.zeros(2, 1, 70)
+    assert drr.reshape_transform(img, batch_size=2).shape == (2, 1, 10, 7)
+    # mutations of model/utils.py:162-171
+    drr.density = None
+    drr.register_buffer("volume", GOLD["hu"])
+    drr.register_buffer("center", torch.zeros(1, 3))
+    assert hasattr(drr, "mask") and drr.affine_inverse(torch.zeros(1, 1, 3)).shape == (1, 1, 3)
+    with pytest.raises(RuntimeError):
+        drr(xvr_b200.convert(GOLD["rot"], GOLD["xyz"], parameterization="euler_angles", convention="ZXY"))
+
+
+def test_no_cpu_fallback():
+    drr = _drr()
+    pose = xvr_b200.convert(GOLD["rot"], GOLD["xyz"], parameterization="euler_angles", convention="ZXY")
+    with pytest.raises(_lib.XvrB200Error):
+        drr(pose)
+    from xvr_b200.metrics import NormalizedCrossCorrelation2d
+
+    with pytest.raises(_lib.XvrB200Error):
+        NormalizedCrossCorrelation2d()(torch.zeros(1, 1, 8, 8), torch.zeros(1, 1, 8, 8))
+
+
+def test_projection_round_trip():
+    drr = _drr()
+    pose = xvr_b200.convert(GOLD["rot"], GOLD["xyz"], parameterization="euler_angles", convention="ZXY")
+    pts = torch.randn(3, 5, 3) * 20
+    uv = drr.perspective_projection(pose, pts)
+    back = drr.inverse_projection(pose, uv)
+    # the back-projected point lies on the source -> point ray
+    src = pose.matrix[:, None, :3, 3]
+    a, b = pts - src, back - src
+    cos = (a * b).sum(-1) / (a.norm(dim=-1) * b.norm(dim=-1))
+    assert torch.allclose(cos, torch.ones_like(cos), atol=1e-5)
+
+
+def test_registration_module():
+    drr = _drr()
+    reg = xvr_b200.Registration(drr, GOLD["rot"][:1], GOLD["xyz"][:1], "euler_angles", "ZXY")
+    assert {n for n, _ in reg.named_parameters()} == {"rotation", "translation"}
+    assert torch.allclose(reg.pose.matrix, xvr_b200.convert(GOLD["rot"][:1], GOLD["xyz"][:1],
+                                                            parameterization="euler_angles", convention="ZXY").matrix)
+
+
+# ------------------------------------------------------------------------------------------------ data / transforms
+def test_hu_to_density_matches_oracle():
+    hu, _, _ = synthetic_ct(24, seed=3)
+    for m in (1.0, 4.5):
+        assert torch.allclose(transform_hu_to_density(hu, m), oracle.hu_to_density(hu, m), atol=1e-7)
+
+
+def test_xray_transforms_match_oracle():
+    g = torch.Generator().manual_seed(0)
+    x = torch.rand(3, 1, 40, 40, generator=g) * 50
+    assert torch.allclose(XrayTransforms(40)(x), oracle.xray_transforms(x, 40), atol=1e-6)
+    assert torch.allclose(XrayTransforms(20, 16)(x), oracle.xray_transforms(x, 20, 16), atol=1e-6)
+    y = XrayTransforms(40, equalize=True)(x)
+    assert y.shape == x.shape and torch.isfinite(y).all()
+
+
+def test_read_centres_the_volume():
+    hu, lab, affine = synthetic_ct(16, with_labels=True)
+    sub = read(hu, lab, labels=[2, 3], affine=affine)
+    assert np.allclose(sub.volume.get_center(), 0.0)
+    assert sub.density.shape == (16, 16, 16) and float(sub.density.max()) <= 1.0
+    assert float(sub.density[lab < 2].abs().max()) == 0.0
