@@ -44,6 +44,17 @@ def peaks():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def measured_traffic(kernel, batch):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/traffic.json), scaled
+    to this batch; None when no capture of this kernel exists."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            rec = json.load(f)[kernel]
+        return rec["dram_bytes_per_launch"] * batch / rec["batch"]
+    except Exception:
+        return None
+
+
 def algorithmic_bytes_fwd(h, w, n_points):
     """SURVEY.md 8(d) gather model: 8 corner voxels x 4 B per sample + the output pixel."""
     return h * w * (n_points * 32 + 4)
@@ -191,8 +202,11 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     workload = (f"{args.vol}^3 synthetic CT (fp32), batch={args.batch} poses per GPU, {args.det}x{args.det} detector, "
                 f"trilinear n_points={N_POINTS}, fwd + bwd w.r.t. 6-DoF pose")
+    vol_mib = args.vol ** 3 * 4 / 2 ** 20
     config = {"workload": workload, "renderer": "trilinear", "parallelism": f"pose-sharded x{world}",
-              "l2_policy": f"volume ({args.vol ** 3 * 4 / 2 ** 20:.0f} MiB) exceeds the 126 MB L2; no flush"}
+              "l2_policy": (f"inputs larger than L2: the {vol_mib:.0f} MiB volume (plus its texture copy) is re-read "
+                            "by every pose; no explicit flush" if vol_mib > 126 else
+                            f"volume ({vol_mib:.0f} MiB) fits in L2: NOT a valid timing configuration")}
 
     if args.impl == "reference":
         if rank != 0:
@@ -253,11 +267,13 @@ def main():
     launches0 = _lib.lib().xvr_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    torch.cuda.profiler.start()  # ncu --profile-from-start off captures exactly the timed steps
     e0.record()
     for _ in range(args.steps):
         step(rot_d, xyz_d)
     e1.record()
     barrier()
+    torch.cuda.profiler.stop()
     ms = e0.elapsed_time(e1)
     launches = _lib.lib().xvr_launch_count() - launches0
     kernel_ms = _lib.stop_profile()
@@ -304,7 +320,8 @@ def main():
             "roofline": {"bound": "hbm", "kernel": "trilinear_fwd_kernel<JAC=true> (one gather pass yields the DRR "
                          "and its per-ray pose Jacobian; the backward is a 28 B/ray epilogue)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg,
+                         "traffic": measured_traffic(name, B) if (H, W, args.vol) == (DET, DET, VOL_N) else None,
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": alg,
                          "kernel_ms": k_avg},
             "roofline_step": {"note": "SURVEY 8(d) fwd+bwd(pose) figure (two gather passes, 2.0977 GB/DRR) over the "
                               "whole step time", "achieved": 2 * alg * args.steps / (ms * 1e-3) / 1e9 / 1.0,

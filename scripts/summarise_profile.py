@@ -1,0 +1,98 @@
+"""Turn the ncu outputs of scripts/gpu_profile.sh (gpurun_out/) into the tracked summaries under profiles/.
+
+    python scripts/summarise_profile.py r1
+"""
+import collections
+import csv
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+tag = sys.argv[1] if len(sys.argv) > 1 else "r1"
+out = os.path.join(ROOT, "profiles")
+os.makedirs(out, exist_ok=True)
+
+KEYS = [
+    "gpu__time_duration.sum", "sm__cycles_elapsed.max", "launch__registers_per_thread", "launch__grid_size",
+    "launch__block_size", "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
+    "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram__cycles_active.avg.pct_of_peak_sustained_elapsed",
+    "lts__t_sector_hit_rate.pct", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+    "lts__t_sectors_srcunit_tex_op_read.sum", "l1tex__t_sector_hit_rate.pct",
+    "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__data_pipe_tex_wavefronts.avg.pct_of_peak_sustained_elapsed",
+    "l1tex__tex_writeback_active.avg.pct_of_peak_sustained_elapsed",
+    "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
+    "l1tex__t_requests_pipe_tex_mem_texture.sum", "l1tex__t_sectors_pipe_tex_mem_texture.sum",
+    "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum",
+    "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+]
+
+
+def raw_page(rep):
+    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(txt.splitlines()))
+    hdr, units = rows[0], rows[1]
+    return [dict(zip(hdr, zip(units, r))) for r in rows[2:]]
+
+
+def summarise_full(rep, name):
+    recs = raw_page(rep)
+    lines = [f"# ncu --set full --clock-control none: {os.path.basename(rep)} ({tag})", ""]
+    traffic = {}
+    for rec in recs:
+        kname = rec["Kernel Name"][1]
+        lines += [f"## {kname}", "", "| metric | unit | value |", "|---|---|---|"]
+        for k in KEYS:
+            if k in rec:
+                lines.append(f"| {k} | {rec[k][0]} | {rec[k][1]} |")
+        def gb(key):
+            u, v = rec[key]
+            scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "Tbyte": 1e12}[u]
+            return float(v.replace(",", "")) * scale
+        t = gb("dram__bytes_read.sum") + gb("dram__bytes_write.sum")
+        traffic[kname] = t
+        lines += ["", f"DRAM traffic (read + write) for this launch: {t / 1e9:.3f} GB", ""]
+    open(os.path.join(out, f"{tag}_{name}_ncu_full.md"), "w").write("\n".join(lines))
+    return traffic
+
+
+def summarise_launches(path):
+    rows = [r for r in csv.reader(open(path)) if len(r) > 10]
+    hdr = rows[0]
+    ki, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+    agg = collections.OrderedDict()
+    for r in rows[1:]:
+        t = float(r[vi].replace(",", "")) * {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}[r[ui]]
+        agg.setdefault(r[ki], []).append(t)
+    tot = sum(sum(v) for v in agg.values())
+    lines = [f"# ncu launch list (gpu__time_duration.sum, --clock-control none) of the timed region of bench.py ({tag})",
+             "", f"total kernel time {tot:.3f} ms over {sum(len(v) for v in agg.values())} launches "
+             "(cold-cache, serialised: compare shares, not absolutes)", "",
+             "| share | total ms | launches | kernel |", "|---|---|---|---|"]
+    for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
+        lines.append(f"| {100 * sum(v) / tot:.2f}% | {sum(v):.3f} | {len(v)} | `{k[:110]}` |")
+    open(os.path.join(out, f"{tag}_launches.md"), "w").write("\n".join(lines) + "\n")
+
+
+g = os.path.join(ROOT, "gpurun_out")
+if os.path.exists(os.path.join(g, "launches.csv")):
+    summarise_launches(os.path.join(g, "launches.csv"))
+tr = {}
+for rep, name, entry in (("prof_trilinear_fwd.ncu-rep", "trilinear_fwd", "xvr_trilinear_drr_fwd"),):
+    if os.path.exists(os.path.join(g, rep)):
+        t = summarise_full(os.path.join(g, rep), name)
+        tr[entry] = {"dram_bytes_per_launch": max(t.values()), "batch": 116,
+                     "source": f"profiles/{tag}_{name}_ncu_full.md"}
+if tr:
+    path = os.path.join(out, "traffic.json")
+    old = json.load(open(path)) if os.path.exists(path) else {}
+    old.update(tr)
+    json.dump(old, open(path, "w"), indent=1)
+for f in ("bench_N1.json", "bench_ref.json"):
+    if os.path.exists(os.path.join(g, f)):
+        open(os.path.join(out, f"{tag}_{f}"), "w").write(open(os.path.join(g, f)).read())
+print(os.listdir(out))

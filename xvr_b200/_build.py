@@ -38,7 +38,8 @@ def build(force=False, verbose=False):
     for src in sources():
         obj = objdir / (src.stem + ".o")
         cmd = [nvcc, *ARCH, "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-Xptxas", "-v",
-               *PER_FILE_FLAGS.get(src.name, []), "-c", str(src), "-o", str(obj)]
+               *PER_FILE_FLAGS.get(src.name, []), *os.environ.get("XVR_B200_NVCC_FLAGS", "").split(),
+               "-c", str(src), "-o", str(obj)]
         procs.append((src, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     objs = []
     log = []

@@ -7,6 +7,15 @@
 // in registers; nothing of size (B, N, n_points) is ever materialised.
 #include "common.cuh"
 
+#ifndef XVR_TRI_MIN_CTAS
+#define XVR_TRI_MIN_CTAS 3
+#endif
+#ifndef XVR_TRI_UNROLL
+#define XVR_TRI_UNROLL 4
+#endif
+#define XVR_PRAGMA(x) _Pragma(#x)
+#define XVR_UNROLL(n) XVR_PRAGMA(unroll n)
+
 namespace xvr {
 
 struct TrilinearParams {
@@ -56,7 +65,7 @@ __device__ __forceinline__ bool misses_padded_box(const float s[3], const float 
 }
 
 template <bool JAC, bool LABELS, bool TEX>
-__global__ void __launch_bounds__(256) trilinear_fwd_kernel(const TrilinearParams p) {
+__global__ void __launch_bounds__(256, XVR_TRI_MIN_CTAS) trilinear_fwd_kernel(const TrilinearParams p) {
   extern __shared__ float chan_acc[];  // LABELS: [C][256]
   const int b = blockIdx.x / p.tiles_per_pose;
   const int tile = blockIdx.x - b * p.tiles_per_pose;
@@ -92,7 +101,7 @@ __global__ void __launch_bounds__(256) trilinear_fwd_kernel(const TrilinearParam
 
   if (!misses_padded_box(s, d, p.vol)) {
     const float lstep = 1.0f / (float)(np - 1);
-#pragma unroll 4
+    XVR_UNROLL(XVR_TRI_UNROLL)
     for (int k = 0; k < np; ++k) {
       const float u = linspace01(k, np, lstep);
       const float alpha = fmaf(u, span, ar.amin);
