@@ -66,6 +66,14 @@ int xvr_trilinear_drr_fwd(const float* volume, const void* voltex, int D0, int D
 int xvr_drr_jac_bwd(const float* jac, const float* gout, const float* det9, int B, int det_h, int det_w, float* gG,
                     void* stream);
 
+/* dL/dvolume of xvr_trilinear_drr_fwd = the `grad_input` half of grid_sampler_3d_backward (fastAtomicAdd scatter,
+ * ATen/native/cuda/GridSampler.cuh:263-280), here in gather form: one owner thread per voxel, no atomics,
+ * deterministic.  vox2cam (B,3,4) = inverse of cam2vox; workspace B*H*W*4 floats; gvol (D0,D1,D2) (+)= gradient. */
+int xvr_trilinear_drr_bwd_volume(const float* cam2vox, const float* vox2cam, const float* cam2world,
+                                 const float* det9, int B, int det_h, int det_w, int n_points, int step_mode,
+                                 float eps, const float* gout, int D0, int D1, int D2, float* workspace, float* gvol,
+                                 int accumulate, void* stream);
+
 /* ---- Siddon renderer = diffdrr.renderers.Siddon.forward (same call sites, --renderer siddon)
  * Traversed voxel indices are bit-identical to the reference's sort + grid_sample(nearest) formulation. */
 int xvr_siddon_rays_fwd(const float* volume, int D0, int D1, int D2, const uint8_t* labels, int C,

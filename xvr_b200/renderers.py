@@ -165,7 +165,8 @@ class _RenderRays(torch.autograd.Function):
 
 class _RenderDRR(torch.autograd.Function):
     """Fused DRR: rays are generated inside the kernel from cam2vox (B,3,4) and the detector basis, so no
-    (B,N,3) tensor exists; the backward reduces the saved per-ray Jacobian straight to dL/dcam2vox (B,3,4)."""
+    (B,N,3) tensor exists; the backward reduces the saved per-ray Jacobian straight to dL/dcam2vox (B,3,4) and,
+    if the volume requires a gradient, gathers dL/dvolume voxel by voxel (no atomics, deterministic)."""
 
     @staticmethod
     def forward(ctx, volume, cam2vox, cam2world, det9, det_hw, args, voltex):
@@ -178,19 +179,30 @@ class _RenderDRR(torch.autograd.Function):
         det = (ctypes.c_float * 9)(*det9)
         call("xvr_trilinear_drr_fwd", ptr(volume), voltex, *volume.shape, ptr(cam2vox), ptr(cam2world), det, B, H, W,
              *args, lw, cw, ptr(out), ptr(jac), stream())
-        if jac is not None:
-            ctx.save_for_backward(jac)
-            ctx.det = (det, B, H, W)
+        ctx.det = (det, B, H, W, args, tuple(volume.shape))
+        ctx.save_for_backward(jac, *((cam2vox, cam2world) if ctx.needs_input_grad[0] else ()))
         return out
 
     @staticmethod
     def backward(ctx, gout):
-        (jac,) = ctx.saved_tensors
-        det, B, H, W = ctx.det
+        jac, *mats = ctx.saved_tensors
+        det, B, H, W, args, shape = ctx.det
         gout = cuda_f32(gout, "grad_output")
-        gG = torch.empty(B, 3, 4, device=gout.device, dtype=torch.float32)
-        call("xvr_drr_jac_bwd", ptr(jac), ptr(gout), det, B, H, W, ptr(gG), stream())
-        return None, gG, None, None, None, None, None
+        gG = gvol = None
+        if ctx.needs_input_grad[1]:
+            gG = torch.empty(B, 3, 4, device=gout.device, dtype=torch.float32)
+            call("xvr_drr_jac_bwd", ptr(jac), ptr(gout), det, B, H, W, ptr(gG), stream())
+        if ctx.needs_input_grad[0]:
+            cam2vox, cam2world = mats
+            full = torch.zeros(B, 4, 4, device=gout.device, dtype=torch.float64)
+            full[:, :3] = cam2vox
+            full[:, 3, 3] = 1.0
+            vox2cam = torch.linalg.inv(full)[:, :3].to(torch.float32).contiguous()
+            work = torch.empty(B * H * W * 4, device=gout.device, dtype=torch.float32)
+            gvol = torch.empty(shape, device=gout.device, dtype=torch.float32)
+            call("xvr_trilinear_drr_bwd_volume", ptr(cam2vox), ptr(vox2cam), ptr(cam2world), det, B, H, W, *args,
+                 ptr(gout), *shape, ptr(work), ptr(gvol), 0, stream())
+        return gvol, gG, None, None, None, None, None
 
 
 class Trilinear(torch.nn.Module):
