@@ -17,7 +17,7 @@ class Standardize(torch.nn.Module):
         self.eps = eps
 
     def forward(self, x):
-        lo, hi = torch.aminmax(x)
+        lo, hi = x.min(), x.max()  # differentiable (aminmax is not)
         return (x - lo) / (hi - lo + self.eps)
 
 
