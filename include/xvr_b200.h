@@ -90,6 +90,10 @@ int xvr_siddon_trace(const float* volume, int D0, int D1, int D2, const float* s
                      int N, float voxel_shift, float eps, int trace_max, int32_t* idx, float* seg, int32_t* count,
                      void* stream);
 
+/* test hook: the hoisted-reciprocal division of the traversal vs IEEE division on random operands;
+ * mismatches is a DEVICE counter the caller zeroes */
+int xvr_selftest_division(int blocks, int per_thread, unsigned seed, unsigned long long* mismatches, void* stream);
+
 /* ---- Similarity = diffdrr.metrics.{NormalizedCrossCorrelation2d, MultiscaleNormalizedCrossCorrelation2d,
  * GradientNormalizedCrossCorrelation2d, Sobel}; call sites /root/reference/src/xvr/model/loss.py:16,27 and
  * /root/reference/src/xvr/registrar/base.py:119-122.

@@ -113,3 +113,11 @@ def test_pose_gradients_match_oracle(cuda, with_labels):
     (oracle_render(drr, r2, x2, renderer="siddon", mask=drr.mask if with_labels else None) * wimg).sum().backward()
     assert rel_l2(r1.grad, r2.grad) < GRAD_TOL
     assert rel_l2(x1.grad, x2.grad) < GRAD_TOL
+
+
+def test_hoisted_reciprocal_division_is_ieee_exact(cuda):
+    """The traversal computes every crossing with a per-ray reciprocal + 3 FMAs; it must equal IEEE division."""
+    bad = torch.zeros(1, dtype=torch.int64, device=cuda)
+    call("xvr_selftest_division", 2048, 256, 12345, ptr(bad), stream())
+    call("xvr_selftest_division", 2048, 256, 777, ptr(bad), stream())
+    assert bad.item() == 0  # 2.7e8 operand pairs

@@ -46,6 +46,7 @@ _SIGNATURES = {
     "xvr_siddon_rays_bwd": (
         [P, c_int, c_int, c_int, P, c_int, P, P, P, c_int, c_int, c_float, c_float, c_int, c_int, c_int, c_int, P, P,
          P, P, P, P], c_int),
+    "xvr_selftest_division": ([c_int, c_int, ctypes.c_uint, P, P], c_int),
     "xvr_siddon_trace": (
         [P, c_int, c_int, c_int, P, P, c_int, c_int, c_float, c_float, c_int, P, P, P, P], c_int),
 }
