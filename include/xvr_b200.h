@@ -68,7 +68,7 @@ int xvr_drr_jac_bwd(const float* jac, const float* gout, const float* det9, int 
 
 /* dL/dvolume of xvr_trilinear_drr_fwd = the `grad_input` half of grid_sampler_3d_backward (fastAtomicAdd scatter,
  * ATen/native/cuda/GridSampler.cuh:263-280), here in gather form: one owner thread per voxel, no atomics,
- * deterministic.  vox2cam (B,3,4) = inverse of cam2vox; workspace B*H*W*4 floats; gvol (D0,D1,D2) (+)= gradient. */
+ * deterministic.  vox2cam (B,3,4) = inverse of cam2vox; workspace 12*B*H*W floats; gvol (D0,D1,D2) (+)= gradient. */
 int xvr_trilinear_drr_bwd_volume(const float* cam2vox, const float* vox2cam, const float* cam2world,
                                  const float* det9, int B, int det_h, int det_w, int n_points, int step_mode,
                                  float eps, const float* gout, int D0, int D1, int D2, float* workspace, float* gvol,

@@ -15,7 +15,7 @@ struct VolGradParams {
   int D0, D1, D2;
   DetectorGeom geom;                  // cam2vox (B,3,4) + detector basis
   const float* __restrict__ vox2cam;  // (B,3,4) inverse of cam2vox
-  const float4* __restrict__ info;    // (B,N) {amin, span, c, 0}
+  const float4* __restrict__ info;    // (B,N,3): {amin, span, c, 0}, {d0, d1, d2, 0}, {1/d0, 1/d1, 1/d2, 0}
   const float* __restrict__ gout;     // (B,N)
   float4* __restrict__ info_out;
   int B, H, W, n_points, step_mode;
@@ -47,7 +47,9 @@ __global__ void __launch_bounds__(256) ray_info_kernel(const VolGradParams p) {
   const float phi[3] = {(float)p.D0, (float)p.D1, (float)p.D2};
   const AlphaRange pr = alpha_range(s, d, plo, phi);
   const float c = (pr.amin < pr.amax) ? __ldg(p.gout + ray) * L * vg_step_weight(p.step_mode, span, p.n_points) : 0.f;
-  p.info_out[ray] = make_float4(ar.amin, span, c, 0.f);
+  p.info_out[ray * 3 + 0] = make_float4(ar.amin, span, c, 0.f);
+  p.info_out[ray * 3 + 1] = make_float4(d[0], d[1], d[2], 0.f);
+  p.info_out[ray * 3 + 2] = make_float4(1.0f / d[0], 1.0f / d[1], 1.0f / d[2], 0.f);
 }
 
 __global__ void __launch_bounds__(256) volume_grad_kernel(const VolGradParams p) {
@@ -88,40 +90,40 @@ __global__ void __launch_bounds__(256) volume_grad_kernel(const VolGradParams p)
     ri = ri * m * fabsf(inv_uy) * 1.01f + 1e-3f;
     const int j0 = max(0, (int)ceilf(cj - rj)), j1 = min(p.W - 1, (int)floorf(cj + rj));
     const int i0 = max(0, (int)ceilf(ci - ri)), i1 = min(p.H - 1, (int)floorf(ci + ri));
+    if (i0 > i1 || j0 > j1) continue;
+    // the source is the translation column of cam2vox (what generate_ray uses)
+    const float* G = p.geom.cam2vox + b * 12;
+    const float s0 = __ldg(G + 3), s1 = __ldg(G + 7), s2 = __ldg(G + 11);
+    const float4* inf = p.info + (int64_t)b * N * 3;
     for (int i = i0; i <= i1; ++i) {
       for (int j = j0; j <= j1; ++j) {
-        const int n = i * p.W + j;
-        const float4 inf = __ldg(p.info + (int64_t)b * N + n);
-        if (inf.z == 0.f) continue;
-        float s[3], d[3], L;
-        generate_ray(p.geom, b, n, p.eps, s, d, L);
+        const float4* q4 = inf + (int64_t)(i * p.W + j) * 3;
+        const float4 a = __ldg(q4);
+        if (a.z == 0.f) continue;
+        const float4 d = __ldg(q4 + 1), r = __ldg(q4 + 2);
         // alpha window in which the ray is within one voxel of p on every axis
-        float alo = -INFINITY, ahi = INFINITY;
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-          const float inv = 1.0f / d[a];
-          const float t0 = (pv[a] - 1.f - s[a]) * inv, t1 = (pv[a] + 1.f - s[a]) * inv;
-          alo = fmaxf(alo, fminf(t0, t1));
-          ahi = fminf(ahi, fmaxf(t0, t1));
-        }
+        const float e0 = pv[0] - s0, e1 = pv[1] - s1, e2 = pv[2] - s2;
+        const float x0 = (e0 - 1.f) * r.x, x1 = (e0 + 1.f) * r.x;
+        const float y0 = (e1 - 1.f) * r.y, y1 = (e1 + 1.f) * r.y;
+        const float z0 = (e2 - 1.f) * r.z, z1 = (e2 + 1.f) * r.z;
+        const float alo = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fminf(z0, z1));
+        const float ahi = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fmaxf(z0, z1));
         if (!(alo < ahi)) continue;
-        // sample indices: alpha_k = amin + u_k span, u_k ~ k/(n-1); widen by one on both sides, test exactly
-        const float sc = (float)(np - 1) / inf.y;
-        const float k0f = (alo - inf.x) * sc, k1f = (ahi - inf.x) * sc;
-        const float klo = fminf(k0f, k1f), khi = fmaxf(k0f, k1f);
-        if (!(khi >= -1.f && klo <= (float)np)) continue;
-        const int ka = max(0, (int)floorf(fmaxf(klo, -1.f)) - 1);
-        const int kb = min(np - 1, (int)ceilf(fminf(khi, (float)np)) + 1);
+        // sample indices: alpha_k = amin + u_k span, u_k ~ k/(n-1); pad the range slightly, the weights decide
+        const float sc = (float)(np - 1) / a.y;
+        const float k0f = (alo - a.x) * sc, k1f = (ahi - a.x) * sc;
+        const float klo = fmaxf(fminf(k0f, k1f) - 0.02f, 0.f), khi = fminf(fmaxf(k0f, k1f) + 0.02f, (float)(np - 1));
+        if (!(klo <= khi)) continue;
         float wsum = 0.f;
-        for (int k = ka; k <= kb; ++k) {
+        for (int k = (int)ceilf(klo); k <= (int)floorf(khi); ++k) {
           const float u = linspace01(k, np, lstep);
-          const float alpha = fmaf(u, inf.y, inf.x);
-          const float dx = fabsf(fmaf(alpha, d[0], s[0]) - pv[0]);
-          const float dy = fabsf(fmaf(alpha, d[1], s[1]) - pv[1]);
-          const float dz = fabsf(fmaf(alpha, d[2], s[2]) - pv[2]);
-          if (dx < 1.f && dy < 1.f && dz < 1.f) wsum += (1.f - dx) * (1.f - dy) * (1.f - dz);
+          const float alpha = fmaf(u, a.y, a.x);
+          const float dx = fabsf(fmaf(alpha, d.x, s0) - pv[0]);
+          const float dy = fabsf(fmaf(alpha, d.y, s1) - pv[1]);
+          const float dz = fabsf(fmaf(alpha, d.z, s2) - pv[2]);
+          if (dx < 1.f && dy < 1.f && dz < 1.f) wsum = fmaf((1.f - dx) * (1.f - dy), 1.f - dz, wsum);
         }
-        acc = fmaf(inf.z, wsum, acc);
+        acc = fmaf(a.z, wsum, acc);
       }
     }
   }
@@ -134,7 +136,7 @@ __global__ void __launch_bounds__(256) volume_grad_kernel(const VolGradParams p)
 using namespace xvr;
 
 // gvol (D0,D1,D2) (+)= dL/dvolume of xvr_trilinear_drr_fwd for upstream gradient gout (B,1,H*W).
-// vox2cam (B,3,4) is the inverse of cam2vox; workspace holds B*H*W float4.  The detector basis must be axis
+// vox2cam (B,3,4) is the inverse of cam2vox; workspace holds 3*B*H*W float4.  The detector basis must be axis
 // aligned in the camera frame (row step along y, column step along x), as DiffDRR's detector is.
 extern "C" int xvr_trilinear_drr_bwd_volume(const float* cam2vox, const float* vox2cam, const float* cam2world,
                                             const float* det9, int B, int det_h, int det_w, int n_points,

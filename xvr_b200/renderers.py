@@ -198,7 +198,7 @@ class _RenderDRR(torch.autograd.Function):
             full[:, :3] = cam2vox
             full[:, 3, 3] = 1.0
             vox2cam = torch.linalg.inv(full)[:, :3].to(torch.float32).contiguous()
-            work = torch.empty(B * H * W * 4, device=gout.device, dtype=torch.float32)
+            work = torch.empty(B * H * W * 12, device=gout.device, dtype=torch.float32)
             gvol = torch.empty(shape, device=gout.device, dtype=torch.float32)
             call("xvr_trilinear_drr_bwd_volume", ptr(cam2vox), ptr(vox2cam), ptr(cam2world), det, B, H, W, *args,
                  ptr(gout), *shape, ptr(work), ptr(gvol), 0, stream())
