@@ -49,6 +49,9 @@ int xvr_trilinear_rays_bwd(const float* volume, const void* voltex, int D0, int 
                            int n_points, int step_mode, float eps, int det_h, int det_w, int lane_w_log2,
                            int cta_w_log2, const float* gout, float* gsource, float* gtarget, float* graylen,
                            float* workspace, void* stream);
+/* lanes sharing one ray in the trilinear forward kernels, as log2 (0..3), -1 = automatic: small batches (B = 1
+ * registration) split each ray's samples over several lanes so that the SMs stay full */
+int xvr_set_ksplit(int ks_log2);
 /* backward through a Jacobian saved by a *_rays_fwd call: 28 bytes per ray instead of a second march */
 int xvr_rays_jac_bwd(const float* jac, const float* gout, int B, int N, float* gsource, float* gtarget,
                      float* graylen, float* workspace, void* stream);

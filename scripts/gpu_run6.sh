@@ -1,2 +1,2 @@
 set -x
-timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -40
+timeout 1500 python -m pytest tests -m gpu -q --durations=12 2>&1 | tail -40

@@ -199,22 +199,33 @@ struct TileMap {
   int lane_w_log2;  // log2 of the warp sub-tile width
   int cta_w_log2;   // log2 of the CTA tile width
   int tiles_x, tiles_y;
+  int ks_log2;      // log2 of the number of lanes that share one ray (each takes a slice of its samples)
 };
 
+// With ks_log2 > 0 a warp holds 32 >> ks_log2 rays; lane l serves ray (l mod rays-per-warp), sample slice
+// l / rays-per-warp (small batches: more threads in flight than rays).
 __device__ __forceinline__ int tile_ray_index(const TileMap& m, int tile, int tid, int N) {
+  const int lane = tid & 31, warp = tid >> 5;
+  const int rpw_log2 = 5 - m.ks_log2;
+  const int r = lane & ((1 << rpw_log2) - 1);
   if (m.W == 0) {
-    int n = tile * 256 + tid;
+    const int n = (tile * 8 + warp) * (1 << rpw_log2) + r;
     return n < N ? n : -1;
   }
-  int lane = tid & 31, warp = tid >> 5;
-  int lw = m.lane_w_log2, cw = m.cta_w_log2;
-  int lane_j = lane & ((1 << lw) - 1), lane_i = lane >> lw;
-  int wpr_log2 = cw - lw;  // warps per tile row
-  int warp_j = warp & ((1 << wpr_log2) - 1), warp_i = warp >> wpr_log2;
-  int ty = tile / m.tiles_x, tx = tile - ty * m.tiles_x;
-  int j = (tx << cw) + (warp_j << lw) + lane_j;
-  int i = ty * (256 >> cw) + warp_i * (32 >> lw) + lane_i;
+  const int lw = m.lane_w_log2, cw = m.cta_w_log2;
+  const int lane_j = r & ((1 << lw) - 1), lane_i = r >> lw;
+  const int wpr_log2 = cw - lw;  // warps per tile row
+  const int warp_j = warp & ((1 << wpr_log2) - 1), warp_i = warp >> wpr_log2;
+  const int ty = tile / m.tiles_x, tx = tile - ty * m.tiles_x;
+  const int j = (tx << cw) + (warp_j << lw) + lane_j;
+  const int i = ty * ((256 >> cw) >> m.ks_log2) + warp_i * ((1 << rpw_log2) >> lw) + lane_i;
   return (i < m.H && j < m.W) ? i * m.W + j : -1;
+}
+
+// sum over the lanes that share a ray (lanes congruent modulo rays-per-warp)
+__device__ __forceinline__ float ksplit_sum(float v, int ks_log2) {
+  for (int o = 16; o >= (32 >> ks_log2); o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

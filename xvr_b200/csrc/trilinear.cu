@@ -74,12 +74,14 @@ __global__ void __launch_bounds__(256, XVR_TRI_MIN_CTAS) trilinear_fwd_kernel(co
   if (LABELS) {
     for (int c = 0; c < p.C; ++c) chan_acc[c * 256 + tid] = 0.f;
   }
-  if (n < 0) return;
-  const int64_t ray = (int64_t)b * p.N + n;
+  const int ks = LABELS ? 0 : p.map.ks_log2;
+  if (n < 0 && ks == 0) return;
+  const bool live = n >= 0;
+  const int64_t ray = (int64_t)b * p.N + (live ? n : 0);
 
   float s[3], d[3], L;
   if (p.fused) {
-    generate_ray(p.geom, b, n, p.eps, s, d, L);
+    generate_ray(p.geom, b, live ? n : 0, p.eps, s, d, L);
   } else {
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
@@ -99,10 +101,14 @@ __global__ void __launch_bounds__(256, XVR_TRI_MIN_CTAS) trilinear_fwd_kernel(co
   float sumV = 0.f;
   float A[3] = {0.f, 0.f, 0.f}, Bv[3] = {0.f, 0.f, 0.f}, T = 0.f, Q = 0.f;
 
-  if (!misses_padded_box(s, d, p.vol)) {
+  // this lane's slice of the samples (all of them unless several lanes share the ray)
+  const int part = (tid & 31) >> (5 - ks);
+  const int kbeg = (int)(((int64_t)np * part) >> ks), kend = (int)(((int64_t)np * (part + 1)) >> ks);
+
+  if (live && !misses_padded_box(s, d, p.vol)) {
     const float lstep = 1.0f / (float)(np - 1);
     XVR_UNROLL(XVR_TRI_UNROLL)
-    for (int k = 0; k < np; ++k) {
+    for (int k = kbeg; k < kend; ++k) {
       const float u = linspace01(k, np, lstep);
       const float alpha = fmaf(u, span, ar.amin);
       const float x = fmaf(alpha, d[0], s[0]);
@@ -127,6 +133,20 @@ __global__ void __launch_bounds__(256, XVR_TRI_MIN_CTAS) trilinear_fwd_kernel(co
         Q = fmaf(u, gd, Q);
       }
     }
+  }
+
+  if (ks > 0) {  // combine the slices (fixed order: deterministic); slice 0 writes
+    sumV = ksplit_sum(sumV, ks);
+    if (JAC) {
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        A[a] = ksplit_sum(A[a], ks);
+        Bv[a] = ksplit_sum(Bv[a], ks);
+      }
+      T = ksplit_sum(T, ks);
+      Q = ksplit_sum(Q, ks);
+    }
+    if (!live || part != 0) return;
   }
 
   if (LABELS) {
@@ -346,6 +366,8 @@ drr_jac_bwd_kernel(const float* __restrict__ jac, const float* __restrict__ gout
   }
 }
 
+static int g_ksplit = -1;  // -1: automatic
+
 static int fill_geom(DetectorGeom& g, const float* cam2vox, const float* cam2world, const float* det9, int W) {
   if (!cam2vox || !cam2world || !det9 || W <= 0) {
     set_last_error("xvr_drr: null geometry argument");
@@ -362,7 +384,8 @@ static int fill_geom(DetectorGeom& g, const float* cam2vox, const float* cam2wor
   return XVR_OK;
 }
 
-static int fill_map(TileMap& m, int N, int det_h, int det_w, int lane_w_log2, int cta_w_log2, int* tiles) {
+static int fill_map(TileMap& m, int N, int det_h, int det_w, int lane_w_log2, int cta_w_log2, int ks_log2,
+                    int* tiles) {
   if (det_w > 0 && det_h > 0) {
     if ((int64_t)det_h * det_w != N) {
       set_last_error("detector hint H*W != N");
@@ -373,11 +396,13 @@ static int fill_map(TileMap& m, int N, int det_h, int det_w, int lane_w_log2, in
       set_last_error("invalid tile shape");
       return XVR_ERR_INVALID;
     }
+    if (ks_log2 > 5 - lane_w_log2) ks_log2 = 5 - lane_w_log2;
     m.W = det_w;
     m.H = det_h;
     m.lane_w_log2 = lane_w_log2;
     m.cta_w_log2 = cta_w_log2;
-    const int tw = 1 << cta_w_log2, th = 256 >> cta_w_log2;
+    m.ks_log2 = ks_log2;
+    const int tw = 1 << cta_w_log2, th = (256 >> cta_w_log2) >> ks_log2;
     m.tiles_x = (det_w + tw - 1) / tw;
     m.tiles_y = (det_h + th - 1) / th;
     *tiles = m.tiles_x * m.tiles_y;
@@ -386,7 +411,8 @@ static int fill_map(TileMap& m, int N, int det_h, int det_w, int lane_w_log2, in
     m.H = 0;
     m.lane_w_log2 = 5;
     m.cta_w_log2 = 8;
-    m.tiles_x = (N + 255) / 256;
+    m.ks_log2 = ks_log2;
+    m.tiles_x = (N + (256 >> ks_log2) - 1) / (256 >> ks_log2);
     m.tiles_y = 1;
     *tiles = m.tiles_x;
   }
@@ -397,7 +423,7 @@ static int fill_common(TrilinearParams& p, const float* volume, const void* volt
                        const uint8_t* labels,
                        int C, const float* source, const float* target, const float* raylen, int B, int N,
                        int n_points, int step_mode, float eps, int det_h, int det_w, int lane_w_log2,
-                       int cta_w_log2) {
+                       int cta_w_log2, bool allow_ksplit = true) {
   if (!volume || ((!source || !target || !raylen) && !p.fused) || B <= 0 || N <= 0 || D0 < 2 || D1 < 2 || D2 < 2 ||
       n_points < 2 || step_mode < 0 || step_mode > 2 || C < 1 || (labels && C > 255) || (!labels && C != 1)) {
     set_last_error("xvr_trilinear: invalid argument");
@@ -432,7 +458,17 @@ static int fill_common(TrilinearParams& p, const float* volume, const void* volt
   p.n_points = n_points;
   p.step_mode = step_mode;
   p.eps = eps;
-  return fill_map(p.map, N, det_h, det_w, lane_w_log2, cta_w_log2, &p.tiles_per_pose);
+  // small batches: let several lanes share a ray so that the machine has >= ~2 waves of threads
+  int ks = 0;
+  if (!labels && allow_ksplit) {
+    if (g_ksplit >= 0) {
+      ks = g_ksplit;
+    } else {
+      const int64_t want = 2LL * 148 * 3 * 256;
+      while (ks < 3 && (((int64_t)B * N) << ks) < want) ++ks;
+    }
+  }
+  return fill_map(p.map, N, det_h, det_w, lane_w_log2, cta_w_log2, ks, &p.tiles_per_pose);
 }
 
 }  // namespace xvr
@@ -484,7 +520,7 @@ extern "C" int xvr_trilinear_rays_bwd(const float* volume, const void* voltex, i
                                       float* gtarget, float* graylen, float* workspace, void* stream) {
   TrilinearParams p = {};
   int rc = fill_common(p, volume, voltex, D0, D1, D2, labels, C, source, target, raylen, B, N, n_points, step_mode, eps,
-                       det_h, det_w, lane_w_log2, cta_w_log2);
+                       det_h, det_w, lane_w_log2, cta_w_log2, false);
   if (rc) return rc;
   if (!gout || !gsource || !gtarget || !graylen || !workspace) {
     set_last_error("xvr_trilinear_rays_bwd: null gradient buffer");
@@ -585,4 +621,15 @@ extern "C" int xvr_drr_jac_bwd(const float* jac, const float* gout, const float*
   if (rc) return rc;
   drr_jac_bwd_kernel<<<B, 1024, 0, (cudaStream_t)stream>>>(jac, gout, det_h * det_w, g, gG);
   return check_launch("xvr_drr_jac_bwd");
+}
+
+// Number of lanes that share one ray in the trilinear forward kernels, as log2 (0..3); -1 = automatic (grow until
+// the launch has about two waves of threads).  Tuning / test hook.
+extern "C" int xvr_set_ksplit(int ks_log2) {
+  if (ks_log2 < -1 || ks_log2 > 3) {
+    set_last_error("xvr_set_ksplit: expected -1 (auto) or 0..3");
+    return XVR_ERR_INVALID;
+  }
+  g_ksplit = ks_log2;
+  return XVR_OK;
 }
