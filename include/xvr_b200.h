@@ -110,6 +110,14 @@ int xvr_ncc_bwd(const float* x1, const float* x2, const float* coef, int which, 
 int xvr_sobel_fwd(const float* x, int B, int H, int W, float* out /* (B,2,H,W) */, void* stream);
 int xvr_sobel_bwd(const float* gout, int B, int H, int W, float* gx /* (B,1,H,W) */, void* stream);
 
+/* ---- HU -> density = diffdrr.data.transform_hu_to_density, called every step at
+ * /root/reference/src/xvr/model/trainer.py:196-197.  xvr_hu_stats reduces {min soft, max soft, min bone, max bone}
+ * once per HU volume (independent of the multiplier; workspace = 4 ints, stats = 4 floats, both DEVICE);
+ * xvr_hu_to_density is the one-pass piecewise map, shifted and scaled to [0,1]. */
+int xvr_hu_stats(const float* hu, long long n, float air, float bone, int* workspace, float* stats, void* stream);
+int xvr_hu_to_density(const float* hu, long long n, float air, float bone, float multiplier, const float* stats,
+                      float* out, void* stream);
+
 /* out[r] = sum_n in[r,n], fixed summation tree */
 int xvr_reduce_rows(const float* in, int rows, int N, float* out, void* stream);
 

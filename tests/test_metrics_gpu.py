@@ -91,3 +91,18 @@ def test_double_geodesic(cuda):
     ref = oracle.double_geodesic(p1.matrix, p2.matrix, 1020.0)
     for a, b in zip(ours, ref):
         assert torch.allclose(a, b, rtol=1e-5, atol=1e-4)
+
+
+def test_hu_to_density_kernel_matches_oracle(cuda):
+    from xvr_b200.data import synthetic_ct, transform_hu_to_density
+
+    hu, _, _ = synthetic_ct(48, seed=5, device=cuda)
+    for m in (1.0, 3.7, 10.0, 0.25):
+        ours = transform_hu_to_density(hu, m)
+        ref = oracle.hu_to_density(hu, m)
+        assert torch.equal(ours, ref), m
+    hu2 = hu.clone()
+    hu2[hu2 > 350] = 100.0  # no bone at all
+    assert torch.equal(transform_hu_to_density(hu2, 5.0), oracle.hu_to_density(hu2, 5.0))
+    hu2.add_(50.0)  # in-place change must invalidate the cached statistics
+    assert torch.equal(transform_hu_to_density(hu2, 2.0), oracle.hu_to_density(hu2, 2.0))

@@ -7,6 +7,8 @@ File IO (NIfTI via torchio) is outside the hot path; ``read`` accepts tensors, a
 is importable.
 """
 
+import weakref
+
 import numpy as np
 import torch
 
@@ -50,12 +52,46 @@ class Subject:
         self.fiducials = fiducials
 
 
+class _HuStats:
+    """{min soft, max soft, min bone, max bone} of the last HU volume seen (they do not depend on the multiplier,
+    and training calls transform_hu_to_density on the same volume every step)."""
+
+    def __init__(self):
+        self.src = None
+        self.version = None
+        self.stats = None
+
+    def get(self, volume):
+        if self.src is None or self.src() is not volume or self.version != volume._version:
+            from ._lib import call, ptr, stream  # noqa: PLC0415
+
+            self.stats = torch.empty(4, device=volume.device, dtype=torch.float32)
+            work = torch.empty(4, device=volume.device, dtype=torch.int32)
+            call("xvr_hu_stats", ptr(volume), volume.numel(), conv.HU_AIR, conv.HU_BONE, ptr(work), ptr(self.stats),
+                 stream())
+            self.src, self.version = weakref.ref(volume), volume._version
+        return self.stats
+
+
+_hu_stats = _HuStats()
+
+
 def transform_hu_to_density(volume, bone_attenuation_multiplier):
     """Piecewise HU -> density map, shifted and scaled to [0,1].
 
     air (HU <= -800) takes the minimum soft-tissue value, soft tissue (-800, 350] is kept, bone (> 350) is
-    multiplied by ``bone_attenuation_multiplier``.
+    multiplied by ``bone_attenuation_multiplier``.  CUDA volumes (the per-step call of the training loop) go
+    through the one-pass kernel of csrc/density.cu; CPU volumes (``read`` at set-up time, before ``.to(device)``)
+    are mapped with tensor ops.
     """
+    if volume.is_cuda:
+        from ._lib import call, ptr, stream  # noqa: PLC0415
+
+        vol = volume if (volume.dtype == torch.float32 and volume.is_contiguous()) else volume.float().contiguous()
+        out = torch.empty_like(vol)
+        call("xvr_hu_to_density", ptr(vol), vol.numel(), conv.HU_AIR, conv.HU_BONE, float(bone_attenuation_multiplier),
+             ptr(_hu_stats.get(vol)), ptr(out), stream())
+        return out
     volume = volume.to(torch.float32)
     soft = (volume > conv.HU_AIR) & (volume <= conv.HU_BONE)
     bone = volume > conv.HU_BONE
