@@ -33,6 +33,30 @@ def test_forward_matches_oracle(cuda, n, h, b):
     assert (img > 0).float().mean() > 0.1
 
 
+@pytest.mark.parametrize("step", ["span/(n-1)", "span/n", "1/n"])
+@pytest.mark.parametrize("n_points", [500, 37])
+def test_step_conventions_and_sample_counts(cuda, step, n_points):
+    """Every setting of the TRILINEAR_STEP knob and a non-default n_points, fwd + grad."""
+    import oracle
+
+    drr = make_drr(48, 24, step=step)
+    rot, xyz = pose_params(2, seed=16)
+    pose = xvr_b200.convert(rot, xyz, parameterization="euler_angles", convention="ZXY")
+    with torch.no_grad():
+        source, target = drr.detector(pose, None)
+        raylen = (target - source).norm(dim=-1).unsqueeze(1)
+        source, target = drr.affine_inverse(source), drr.affine_inverse(target)
+    outs = []
+    for fn in (lambda s, t: drr.renderer(drr.density, s, t, raylen, n_points=n_points),
+               lambda s, t: oracle.trilinear_render(drr.density, s, t, raylen, n_points=n_points, step=step)):
+        s, t = source.clone().requires_grad_(), target.clone().requires_grad_()
+        img = fn(s, t)
+        img.sum().backward()
+        outs.append((img.detach(), s.grad, t.grad))
+    assert rel_l2(outs[0][0], outs[1][0]) < FWD_TOL
+    assert rel_l2(outs[0][1], outs[1][1]) < GRAD_TOL and rel_l2(outs[0][2], outs[1][2]) < GRAD_TOL
+
+
 def test_forward_config1_cpu_oracle(cuda):
     """BASELINE config 1: 128^3, 4 poses, 64x64 trilinear DRR, oracle on the CPU (reference's own runnable case)."""
     drr = make_drr(128, 64)
