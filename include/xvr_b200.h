@@ -93,6 +93,10 @@ int xvr_siddon_trace(const float* volume, int D0, int D1, int D2, const float* s
                      int N, float voxel_shift, float eps, int trace_max, int32_t* idx, float* seg, int32_t* count,
                      void* stream);
 
+/* test hook: scale of the per-ray tolerance that certifies the fast voxel index of the traversal (1 = production;
+ * a huge value, e.g. 1e30, routes every segment through the reference's exact normalise/un-normalise arithmetic) */
+int xvr_set_siddon_index_tol_scale(float scale);
+
 /* test hook: the hoisted-reciprocal division of the traversal vs IEEE division on random operands;
  * mismatches is a DEVICE counter the caller zeroes */
 int xvr_selftest_division(int blocks, int per_thread, unsigned seed, unsigned long long* mismatches, void* stream);

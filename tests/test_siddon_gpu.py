@@ -121,3 +121,36 @@ def test_hoisted_reciprocal_division_is_ieee_exact(cuda):
     call("xvr_selftest_division", 2048, 256, 12345, ptr(bad), stream())
     call("xvr_selftest_division", 2048, 256, 777, ptr(bad), stream())
     assert bad.item() == 0  # 2.7e8 operand pairs
+
+
+def _trace_digest(drr, source, target, shift, scale, max_seg):
+    """Per-ray digests of the traversal (segment count, sum of voxel indices, sum of idx * position) computed with
+    the fast-index certificate tolerance scaled by `scale`."""
+    call("xvr_set_siddon_index_tol_scale", float(scale))
+    try:
+        idx, seg, cnt = _trace(drr.density, source, target, shift, max_seg)
+    finally:
+        call("xvr_set_siddon_index_tol_scale", 1.0)
+    return idx, seg, cnt
+
+
+@pytest.mark.parametrize("n,h,b,shift,stretch", [(256, 160, 6, 0.5, 1.0), (200, 128, 4, 0.0, 1.0),
+                                                  (96, 64, 8, 0.25, 1.0), (256, 128, 4, 0.5, 7.0)])
+def test_fast_index_equals_exact_index(cuda, n, h, b, shift, stretch):
+    """Every voxel index certified by the cheap path equals the reference's exact normalise / un-normalise /
+    nearbyint arithmetic (index_tol_scale = 1e30 routes ALL segments through the exact path): tens of millions of
+    segments, including source positions several thousand voxels away (the rounding budget scales with them)."""
+    drr = make_drr(n, h, renderer="siddon", voxel_shift=shift)
+    rot, xyz = pose_params(b, seed=23)
+    source, target, _ = _rays(drr, rot, xyz)
+    if stretch != 1.0:  # same lines, the source `stretch` times further away (~5600 voxels): larger rounding budget
+        centre = target.mean(1, keepdim=True)
+        source = (centre + stretch * (source - centre)).contiguous()
+    M = 3 * n + 8
+    idx_f, seg_f, cnt_f = _trace_digest(drr, source, target, shift, 1.0, M)
+    idx_e, seg_e, cnt_e = _trace_digest(drr, source, target, shift, 1e30, M)
+    assert cnt_f.max().item() <= M
+    assert torch.equal(cnt_f, cnt_e)
+    assert torch.equal(seg_f, seg_e)
+    assert torch.equal(idx_f, idx_e)
+    assert cnt_f.sum().item() > 2_000_000
