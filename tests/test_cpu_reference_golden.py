@@ -1,0 +1,58 @@
+"""Pins against vectors produced by the GENUINE reference code (tests/golden/make_reference_golden.py): the two
+hot-path files of xvr that import without DiffDRR -- utils/preprocess.py and
+model/scheduler.py.  Oracle AND product are both held to them; tolerance: fp32 round-off of re-associated sums."""
+
+import os
+
+import pytest
+import torch
+
+import oracle
+from xvr_b200.preprocess import Equalize, Standardize, XrayTransforms
+from xvr_b200.trainer import WarmupCosineSchedule
+
+GOLD = torch.load(os.path.join(os.path.dirname(__file__), "golden", "reference_v1.pt"), weights_only=False)
+TOL = 2e-6
+
+
+def _close(a, b, tol=TOL):
+    assert a.shape == b.shape
+    assert (a - b).abs().max().item() <= tol * max(1.0, b.abs().max().item())
+
+
+@pytest.mark.parametrize("case", sorted(GOLD["xray_transforms"]["cases"]))
+def test_xray_transforms_match_the_reference(case):
+    x = GOLD["xray_transforms"]["x"]
+    c = GOLD["xray_transforms"]["cases"][case]
+    _close(XrayTransforms(**c["kwargs"])(x), c["out"])
+    if not c["kwargs"].get("equalize"):
+        kw = dict(c["kwargs"])
+        _close(oracle.xray_transforms(x, kw.pop("height"), kw.pop("width", None), **kw), c["out"])
+
+
+def test_standardize_and_equalize_match_the_reference():
+    s = GOLD["standardize"]
+    _close(Standardize()(s["x"]), s["out"])
+    _close(Standardize(eps=1e-3)(s["x"]), s["out_eps"])
+    _close(oracle.standardize(s["x"]), s["out"])
+    e = GOLD["equalize"]
+    _close(Equalize()(e["x"]), e["out"], 1e-5)
+    _close(Equalize(n_bins=32, tau=0.05)(e["x"]), e["out_coarse"], 1e-5)
+
+
+def _lrs(make, steps):
+    p = torch.nn.Parameter(torch.zeros(1))
+    opt = torch.optim.Adam([p], lr=2e-4)
+    s = make(opt)
+    seq = [s.get_last_lr()[0]]
+    for _ in range(steps):
+        opt.step()
+        s.step()
+        seq.append(s.get_last_lr()[0])
+    return torch.tensor(seq, dtype=torch.float64)
+
+
+def test_warmup_cosine_schedule_matches_the_reference():
+    g = GOLD["schedule"]
+    assert torch.equal(_lrs(lambda o: WarmupCosineSchedule(o, 250, 2500), 300), g["warmup_cosine_250_of_2500"])
+    assert torch.equal(_lrs(lambda o: WarmupCosineSchedule(o, 2.5, 40.0), 45), g["warmup_cosine_fractional"])
