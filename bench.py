@@ -206,7 +206,9 @@ def main():
     config = {"workload": workload, "renderer": "trilinear", "parallelism": f"pose-sharded x{world}",
               "l2_policy": (f"inputs larger than L2: the {vol_mib:.0f} MiB volume (plus its texture copy) is re-read "
                             "by every pose; no explicit flush" if vol_mib > 126 else
-                            f"volume ({vol_mib:.0f} MiB) fits in L2: NOT a valid timing configuration")}
+                            f"volume ({vol_mib:.0f} MiB) fits in L2: NOT a valid timing configuration"),
+              "e2e_pipeline": "poses H2D from pinned memory, DRRs + pose gradients D2H to pinned memory every step; "
+                              "double-buffered (copy of step i overlaps the render of step i+1, host reads step i-1)"}
 
     if args.impl == "reference":
         if rank != 0:
@@ -278,19 +280,41 @@ def main():
     launches = _lib.lib().xvr_launch_count() - launches0
     kernel_ms = _lib.stop_profile()
 
-    # ---- end-to-end timing through the public API with host buffers ("e2e")
+    # ---- end-to-end timing through the public API with host buffers ("e2e"): every step copies its poses in from
+    # pinned memory and its DRRs + pose gradients out to pinned memory.  Double-buffered: the device->host copy of
+    # step i runs on a copy stream while step i+1 renders, and the host consumes (waits for) the result of step
+    # i-1 before it queues step i+1 -- every copy and every wait is inside the timed region.
+    img_hh = [img_h, torch.empty_like(img_h).pin_memory()]
+    grad_hh = [grad_h, torch.empty_like(grad_h).pin_memory()]
+    copy_stream = torch.cuda.Stream(device=device)
+    done = [torch.cuda.Event(), torch.cuda.Event()]
+    main_stream = torch.cuda.current_stream()
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
-    for _ in range(args.steps):
+    keep = [None, None]
+    checksum = 0.0
+    for i in range(args.steps):
         r, x = rot_h.to(device, non_blocking=True), xyz_h.to(device, non_blocking=True)
         img, gr, gx = step(r, x)
-        img_h.copy_(img, non_blocking=True)
-        grad_h[:, :3].copy_(gr, non_blocking=True)
-        grad_h[:, 3:].copy_(gx, non_blocking=True)
-        torch.cuda.current_stream().synchronize()  # the caller reads the result every step
+        g6 = torch.cat([gr, gx], dim=1)  # one contiguous (B,6) block: a strided D2H copy would be staged + synchronous
+        ready = torch.cuda.Event()
+        ready.record(main_stream)
+        slot = i & 1
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(ready)
+            img_hh[slot].copy_(img, non_blocking=True)
+            grad_hh[slot].copy_(g6, non_blocking=True)
+            done[slot].record(copy_stream)
+        keep[slot] = (img, g6)  # keep the device tensors alive until their copy has run
+        if i > 0:  # the caller reads the previous step's result while this one renders
+            done[slot ^ 1].synchronize()
+            checksum += float(img_hh[slot ^ 1][0, 0, H // 2, W // 2]) + float(grad_hh[slot ^ 1][0, 0])
+    done[(args.steps - 1) & 1].synchronize()
+    checksum += float(img_hh[(args.steps - 1) & 1][0, 0, H // 2, W // 2])
     e3.record()
     barrier()
+    assert checksum == checksum, "e2e result is NaN"
     ms_e2e = e2.elapsed_time(e3)
     clocks = sampler.stop() if rank == 0 else None
 

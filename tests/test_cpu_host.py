@@ -231,3 +231,20 @@ def test_read_centres_the_volume():
     assert np.allclose(sub.volume.get_center(), 0.0)
     assert sub.density.shape == (16, 16, 16) and float(sub.density.max()) <= 1.0
     assert float(sub.density[lab < 2].abs().max()) == 0.0
+
+
+def test_evaluator_metrics():
+    """xvr's Evaluator (metrics/evaluator.py): zero for identical poses; a pure in-plane shift of t mm gives
+    mTRE = t, mPE = t * sdd / depth (magnification) and a positive geodesic."""
+    from xvr_b200.evaluator import Evaluator
+
+    drr = _drr()
+    fid = torch.tensor([[[0.0, 0.0, 0.0], [10.0, -5.0, 8.0], [-12.0, 6.0, -7.0]]])
+    rot, xyz = torch.zeros(1, 3), torch.tensor([[0.0, 800.0, 0.0]])
+    true = xvr_b200.convert(rot, xyz, parameterization="euler_angles", convention="ZXY")
+    assert Evaluator(drr, fid)(true, true) == pytest.approx([0.0, 0.0, 0.0, 0.0], abs=1e-3)
+    pred = xvr_b200.convert(rot, xyz + torch.tensor([[3.0, 0.0, 0.0]]), parameterization="euler_angles", convention="ZXY")
+    mpe, mrpe, mtre, dgeo = Evaluator(drr, fid)(true, pred)
+    assert mtre == pytest.approx(3.0, abs=1e-3)
+    assert 3.0 < mpe < 3.0 * 1020.0 / 700.0  # magnified by sdd / depth, depth in (700, 900) for these fiducials
+    assert mrpe > 0 and dgeo == pytest.approx(3.0, abs=1e-3)
