@@ -34,12 +34,13 @@ extern "C" int xvr_abi_version(void) { return 1; }
 extern "C" long long xvr_launch_count(void) { return xvr::g_launches; }
 
 // ---------------------------------------------------------------------------------------------- volume texture
-// A second, block-linear copy of the CT volume (cudaArray, layered 2D: layer = axis 0) behind a point-sampled
-// texture object.  The trilinear kernels fetch the 2x2 (axis 1, axis 2) corner footprint of each of the two
+// A second, block-linear copy of the CT volume (cudaArray, layered 2D: layer = axis 0 + 1, with one zero layer at
+// each end) behind a point-sampled texture object.  The trilinear kernels fetch the 2x2 (axis 1, axis 2) corner footprint of each of the two
 // layers with one TLD4 each instead of 8 scalar loads.
 extern "C" int xvr_volume_create(int D0, int D1, int D2, void** out) {
-  if (!out || D0 < 1 || D1 < 1 || D2 < 1 || D0 > 2048 || D1 > 32768 || D2 > 32768) {
-    xvr::set_last_error("xvr_volume_create: invalid shape (layered 2D arrays hold <= 2048 layers of <= 32768^2)");
+  if (!out || D0 < 1 || D1 < 1 || D2 < 1 || D0 > 2046 || D1 > 32768 || D2 > 32768) {
+    xvr::set_last_error("xvr_volume_create: invalid shape (layered 2D arrays hold <= 2048 layers of <= 32768^2, "
+                        "two of which are the zero padding)");
     return XVR_ERR_INVALID;
   }
   xvr::VolumeTexture* vt = new xvr::VolumeTexture();
@@ -47,7 +48,23 @@ extern "C" int xvr_volume_create(int D0, int D1, int D2, void** out) {
   vt->D1 = D1;
   vt->D2 = D2;
   cudaChannelFormatDesc desc = cudaCreateChannelDesc<float>();
-  cudaError_t e = cudaMalloc3DArray(&vt->array, &desc, make_cudaExtent(D2, D1, D0), cudaArrayLayered);
+  cudaError_t e = cudaMalloc3DArray(&vt->array, &desc, make_cudaExtent(D2, D1, D0 + 2), cudaArrayLayered);
+  if (e == cudaSuccess) {  // zero the two padding layers (0 and D0 + 1) once; uploads never touch them
+    float* zeros = nullptr;
+    e = cudaMalloc(&zeros, (size_t)D1 * D2 * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemset(zeros, 0, (size_t)D1 * D2 * sizeof(float));
+    for (int layer = 0; layer <= D0 + 1 && e == cudaSuccess; layer += D0 + 1) {
+      cudaMemcpy3DParms cp = {};
+      cp.srcPtr = make_cudaPitchedPtr(zeros, (size_t)D2 * sizeof(float), D2, D1);
+      cp.dstArray = vt->array;
+      cp.dstPos = make_cudaPos(0, 0, layer);
+      cp.extent = make_cudaExtent(D2, D1, 1);
+      cp.kind = cudaMemcpyDeviceToDevice;
+      e = cudaMemcpy3D(&cp);
+    }
+    if (zeros) cudaFree(zeros);
+    if (e != cudaSuccess) cudaFreeArray(vt->array);
+  }
   if (e == cudaSuccess) {
     cudaResourceDesc rd = {};
     rd.resType = cudaResourceTypeArray;
@@ -81,6 +98,7 @@ extern "C" int xvr_volume_upload(void* handle, const float* volume, void* stream
   cudaMemcpy3DParms cp = {};
   cp.srcPtr = make_cudaPitchedPtr((void*)volume, (size_t)vt->D2 * sizeof(float), vt->D2, vt->D1);
   cp.dstArray = vt->array;
+  cp.dstPos = make_cudaPos(0, 0, 1);  // array layer 0 is zero padding
   cp.extent = make_cudaExtent(vt->D2, vt->D1, vt->D0);
   cp.kind = cudaMemcpyDeviceToDevice;
   cudaError_t e = cudaMemcpy3DAsync(&cp, (cudaStream_t)stream);

@@ -24,6 +24,8 @@ struct Vol {
 };
 
 // Opaque handle behind xvr_volume_* (include/xvr_b200.h): a block-linear layered array + point-sampled texture.
+// The array has D0 + 2 layers: volume layer x lives in array layer x + 1, array layers 0 and D0 + 1 are zero, so
+// that grid_sample's zero padding along axis 0 is a clamped layer index instead of a predicated fetch.
 struct VolumeTexture {
   cudaArray_t array;
   cudaTextureObject_t tex;
@@ -127,12 +129,13 @@ __device__ __forceinline__ float sample_trilinear(const Vol& v, float x, float y
   float fx = x - fx0, fy = y - fy0, fz = z - fz0;
   float c000, c001, c010, c011, c100, c101, c110, c111;
   if (TEX) {
-    // two gathers fetch the 8 corners; axis-1/2 padding comes from the border mode, axis-0 from the predicates
-    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    // two unconditional gathers fetch the 8 corners; axis-1/2 padding comes from the border mode, axis-0 padding
+    // from the zero layers at both ends of the array (any out-of-range x clamps onto one of them)
     const float tu = fz0 + 1.0f, tv = fy0 + 1.0f;
-    if ((unsigned)ix < (unsigned)v.D0) a = gather_yz(v.tex, ix, tu, tv);
+    const unsigned last = (unsigned)(v.D0 + 1);
+    const float4 a = gather_yz(v.tex, (int)min((unsigned)(ix + 1), last), tu, tv);
+    const float4 b = gather_yz(v.tex, (int)min((unsigned)(ix + 2), last), tu, tv);
     c010 = a.x; c011 = a.y; c001 = a.z; c000 = a.w;
-    if ((unsigned)(ix + 1) < (unsigned)v.D0) b = gather_yz(v.tex, ix + 1, tu, tv);
     c110 = b.x; c111 = b.y; c101 = b.z; c100 = b.w;
   } else if ((unsigned)ix < (unsigned)(v.D0 - 1) && (unsigned)iy < (unsigned)(v.D1 - 1) &&
       (unsigned)iz < (unsigned)(v.D2 - 1)) {

@@ -98,8 +98,10 @@ __global__ void __launch_bounds__(256, XVR_TRI_MIN_CTAS) trilinear_fwd_kernel(co
   const float span = ar.amax - ar.amin;
   const float w = step_weight(p.step_mode, span, np);
 
+  // Running sums.  With JAC: A = sum grad V, U = sum u grad V; everything else the Jacobian needs is linear in
+  // them (alpha_k = amin + u_k span): sum alpha grad V = amin A + span U, sum grad V . d = d . A, sum u grad V . d = d . U.
   float sumV = 0.f;
-  float A[3] = {0.f, 0.f, 0.f}, Bv[3] = {0.f, 0.f, 0.f}, T = 0.f, Q = 0.f;
+  float A[3] = {0.f, 0.f, 0.f}, U[3] = {0.f, 0.f, 0.f};
 
   // this lane's slice of the samples (all of them unless several lanes share the ray)
   const int part = (tid & 31) >> (5 - ks);
@@ -107,9 +109,7 @@ __global__ void __launch_bounds__(256, XVR_TRI_MIN_CTAS) trilinear_fwd_kernel(co
 
   if (live && !misses_padded_box(s, d, p.vol)) {
     const float lstep = 1.0f / (float)(np - 1);
-    XVR_UNROLL(XVR_TRI_UNROLL)
-    for (int k = kbeg; k < kend; ++k) {
-      const float u = linspace01(k, np, lstep);
+    auto sample = [&](float u) {
       const float alpha = fmaf(u, span, ar.amin);
       const float x = fmaf(alpha, d[0], s[0]);
       const float y = fmaf(alpha, d[1], s[1]);
@@ -126,13 +126,21 @@ __global__ void __launch_bounds__(256, XVR_TRI_MIN_CTAS) trilinear_fwd_kernel(co
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
           A[a] += g[a];
-          Bv[a] = fmaf(alpha, g[a], Bv[a]);
+          U[a] = fmaf(u, g[a], U[a]);
         }
-        const float gd = fmaf(g[0], d[0], fmaf(g[1], d[1], g[2] * d[2]));
-        T += gd;
-        Q = fmaf(u, gd, Q);
       }
-    }
+    };
+    // torch.linspace evaluates the two halves of [0,1] from their own ends (linspace01): one loop per half, each
+    // with a float counter, instead of a select + int->float conversion per sample
+    const int half = np / 2;
+    int k = kbeg;
+    const int k1 = min(kend, half);
+    float kf = (float)k;
+    XVR_UNROLL(XVR_TRI_UNROLL)
+    for (; k < k1; ++k, kf += 1.0f) sample(lstep * kf);
+    float rf = (float)(np - 1 - k);
+    XVR_UNROLL(XVR_TRI_UNROLL)
+    for (; k < kend; ++k, rf -= 1.0f) sample(1.0f - lstep * rf);
   }
 
   if (ks > 0) {  // combine the slices (fixed order: deterministic); slice 0 writes
@@ -141,10 +149,8 @@ __global__ void __launch_bounds__(256, XVR_TRI_MIN_CTAS) trilinear_fwd_kernel(co
 #pragma unroll
       for (int a = 0; a < 3; ++a) {
         A[a] = ksplit_sum(A[a], ks);
-        Bv[a] = ksplit_sum(Bv[a], ks);
+        U[a] = ksplit_sum(U[a], ks);
       }
-      T = ksplit_sum(T, ks);
-      Q = ksplit_sum(Q, ks);
     }
     if (!live || part != 0) return;
   }
@@ -164,13 +170,16 @@ __global__ void __launch_bounds__(256, XVR_TRI_MIN_CTAS) trilinear_fwd_kernel(co
     // dI/ds = L [ sumV w' (dspan/ds) + w (A - Bv + P damin/ds + Q damax/ds) ],  P = T - Q
     // dI/dt = L [ sumV w' (dspan/dt) + w (     Bv + P damin/dt + Q damax/dt) ]
     // a crossing alpha = (plane - s_a)/d_a has dalpha/ds_a = (alpha-1)/d_a, dalpha/dt_a = -alpha/d_a.
+    const float T = fmaf(A[0], d[0], fmaf(A[1], d[1], A[2] * d[2]));
+    const float Q = fmaf(U[0], d[0], fmaf(U[1], d[1], U[2] * d[2]));
     const float P = T - Q;
     const float wp = step_weight_dspan(p.step_mode, np);
     float js[3], jt[3];
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-      js[a] = w * (A[a] - Bv[a]);
-      jt[a] = w * Bv[a];
+      const float Bv = fmaf(ar.amin, A[a], span * U[a]);
+      js[a] = w * (A[a] - Bv);
+      jt[a] = w * Bv;
     }
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
