@@ -37,7 +37,8 @@ int xvr_volume_destroy(void* handle);
  * call site /root/reference/src/xvr/model/trainer.py:288  drr.renderer(vol, source, target, raylen, mask=seg)
  *   source (B,1,3), target (B,N,3), raylen (B,N); labels (D0,D1,D2) uint8 or NULL with C = max label + 1 (else 1)
  *   step_mode 0: span/(n-1)  1: span/n  2: 1/n ;  det_h*det_w == N selects compact detector tiles (0,0 = linear)
- *   out (B,C,N);  jac (B,7,N) or NULL: per-ray d out/d(source xyz, target xyz, raylen) (only without labels) */
+ *   out (B,C,N);  jac (B,7,N) or NULL: per-ray d(sum over channels of out)/d(source xyz, target xyz, raylen) --
+ *   with labels this serves callers that collapse the channels (trainer.py:294), others use xvr_*_rays_bwd */
 int xvr_trilinear_rays_fwd(const float* volume, const void* voltex, int D0, int D1, int D2, const uint8_t* labels,
                            int C, const float* source, const float* target, const float* raylen, int B, int N,
                            int n_points, int step_mode, float eps, int det_h, int det_w, int lane_w_log2,

@@ -29,6 +29,12 @@ KEYS = [
     "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
     "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
     "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active", "smsp__thread_inst_executed_per_inst_executed.ratio",
+    "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_tex_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
 ]
 
 
@@ -87,6 +93,16 @@ for rep, name, entry in (("prof_trilinear_fwd.ncu-rep", "trilinear_fwd", "xvr_tr
         t = summarise_full(os.path.join(g, rep), name)
         tr[entry] = {"dram_bytes_per_launch": max(t.values()), "batch": 116,
                      "source": f"profiles/{tag}_{name}_ncu_full.md"}
+for rep, name in (("prof_siddon_fwd.ncu-rep", "siddon_fwd"), ("prof_volgrad.ncu-rep", "volume_grad")):
+    if os.path.exists(os.path.join(g, rep)):
+        summarise_full(os.path.join(g, rep), name)
+if os.path.exists(os.path.join(g, "kernels.log")):
+    body = open(os.path.join(g, "kernels.log")).read()
+    table = body[body.index("| kernel |"):] if "| kernel |" in body else body
+    open(os.path.join(out, f"{tag}_kernels.md"), "w").write(
+        f"# scripts/bench_kernels.py on 1xB200 ({tag}): CUDA-event time per call, algorithmic bytes per SURVEY 8(d)\n\n"
+        "Configs: trilinear = C2 (512^3, 256^2, B=116, n=500); siddon = C5 geometry (768^3, 512^2) at B=32; "
+        "NCC = 116 images of 256^2.\n\n" + table)
 if tr:
     path = os.path.join(out, "traffic.json")
     old = json.load(open(path)) if os.path.exists(path) else {}

@@ -329,3 +329,28 @@ def test_errors_are_loud(cuda):
         drr.renderer(drr.density.cpu(), source.cpu(), target.cpu(), torch.ones(1, 1, 256))
     with pytest.raises(ValueError):
         drr.renderer(drr.density, source, target, torch.ones(1, 1, 3, device=cuda))
+
+
+@pytest.mark.parametrize("renderer", ["trilinear", "siddon"])
+def test_channel_collapsed_gradient_uses_the_saved_jacobian(cuda, renderer):
+    """trainer.py:292-294 collapses the label channels right after rendering (img.sum(dim=1)); autograd then hands
+    the renderer one shared upstream gradient (stride 0 along the channels) and the backward is the Jacobian
+    epilogue.  It must equal the per-channel recompute backward fed the same (materialised) gradient, and the
+    gradient of the unlabelled render."""
+    drr = make_drr(64, 32, renderer=renderer, with_labels=True)
+    rot, xyz = pose_params(3, seed=6)
+    w = torch.rand(3, 1, 32, 32, generator=torch.Generator().manual_seed(1)).to(cuda)
+    grads = []
+    for mode in ("collapsed", "materialised", "unlabelled"):
+        r, x = rot.clone().requires_grad_(), xyz.clone().requires_grad_()
+        pose = xvr_b200.convert(r, x, parameterization="euler_angles", convention="ZXY")
+        if mode == "unlabelled":
+            img = drr(pose)
+        else:
+            img = drr(pose, mask_to_channels=True)
+            assert img.shape[1] > 1
+            img = img.sum(dim=1, keepdim=True) if mode == "collapsed" else (img * torch.ones_like(img)).sum(1, keepdim=True)
+        (img * w).sum().backward()
+        grads.append(torch.cat([r.grad, x.grad], 1))
+    assert rel_l2(grads[0], grads[1]) < 1e-4
+    assert rel_l2(grads[0], grads[2]) < 1e-4

@@ -493,8 +493,8 @@ extern "C" int xvr_trilinear_rays_fwd(const float* volume, const void* voltex, i
   int rc = fill_common(p, volume, voltex, D0, D1, D2, labels, C, source, target, raylen, B, N, n_points, step_mode, eps,
                        det_h, det_w, lane_w_log2, cta_w_log2);
   if (rc) return rc;
-  if (!out || (jac && labels)) {
-    set_last_error("xvr_trilinear_rays_fwd: out is null, or jac requested together with labels");
+  if (!out) {
+    set_last_error("xvr_trilinear_rays_fwd: out is null");
     return XVR_ERR_INVALID;
   }
   p.out = out;
@@ -508,7 +508,9 @@ extern "C" int xvr_trilinear_rays_fwd(const float* volume, const void* voltex, i
   const size_t smem = labels ? (size_t)C * 256 * sizeof(float) : 0;
   const bool tex = p.vol.tex != 0;
   if (labels) {
-    auto k = tex ? trilinear_fwd_kernel<false, true, true> : trilinear_fwd_kernel<false, true, false>;
+    // with jac: the Jacobian of the channel SUM (what a caller that collapses the channels differentiates)
+    auto k = jac ? (tex ? trilinear_fwd_kernel<true, true, true> : trilinear_fwd_kernel<true, true, false>)
+                 : (tex ? trilinear_fwd_kernel<false, true, true> : trilinear_fwd_kernel<false, true, false>);
     if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k<<<(unsigned)grid, 256, smem, st>>>(p);
   } else if (jac) {

@@ -128,33 +128,34 @@ class _RenderRays(torch.autograd.Function):
         det_h, det_w = det_hw if det_hw is not None and det_hw[0] * det_hw[1] == N else (0, 0)
         need_pose_grad = any(ctx.needs_input_grad[1:4])
         out = torch.empty(B, C, N, device=volume.device, dtype=torch.float32)
-        jac = None
-        if need_pose_grad and labels is None:
-            jac = torch.empty(B, 7, N, device=volume.device, dtype=torch.float32)
+        # with label channels the Jacobian is the one of the channel SUM: enough whenever the caller collapses the
+        # channels (trainer.py:294 img.sum(dim=1)); backward() falls back to the recompute kernel otherwise
+        jac = torch.empty(B, 7, N, device=volume.device, dtype=torch.float32) if need_pose_grad else None
         vol_args = (ptr(volume),) if voltex is False else (ptr(volume), voltex)
         ctx.common = (*vol_args, *volume.shape, ptr(labels), C, ptr(source), ptr(target), ptr(raylen), B, N, *args,
                       det_h, det_w, lw, cw)
         call(f"xvr_{kind}_rays_fwd", *ctx.common, ptr(out), ptr(jac), stream())
         ctx.kind = kind
-        if jac is not None:
-            ctx.save_for_backward(jac)
-            ctx.mode = "jac"
-        elif need_pose_grad:
-            ctx.save_for_backward(volume, source, target, raylen, labels)  # keeps the raw pointers alive
-            ctx.mode = "recompute"
+        if need_pose_grad:
+            # the recompute path (per-channel upstream gradients) needs the inputs; saving them keeps the raw
+            # pointers of ctx.common alive
+            ctx.save_for_backward(jac, *((volume, source, target, raylen, labels) if labels is not None else ()))
         return out
 
     @staticmethod
     def backward(ctx, gout):
-        gout = cuda_f32(gout, "grad_output")
+        gout_shared = gout.shape[1] == 1 or gout.stride(1) == 0
+        gout = cuda_f32(gout[:, :1] if gout_shared else gout, "grad_output")
         B, _, N = gout.shape
         dev = gout.device
         gsource = torch.empty(B, 1, 3, device=dev, dtype=torch.float32)
         gtarget = torch.empty(B, N, 3, device=dev, dtype=torch.float32)
         graylen = torch.empty(B, 1, N, device=dev, dtype=torch.float32)
         work = torch.empty(B, 3, N, device=dev, dtype=torch.float32)
-        if ctx.mode == "jac":
-            (jac,) = ctx.saved_tensors
+        jac = ctx.saved_tensors[0]
+        # One upstream gradient per ray: single channel, or every channel sees the same gradient -- autograd hands
+        # the backward of sum(dim=1) over as an expanded view (stride 0 along the channel axis), a host-side check.
+        if gout_shared:
             call("xvr_rays_jac_bwd", ptr(jac), ptr(gout), B, N, ptr(gsource), ptr(gtarget), ptr(graylen),
                  ptr(work), stream())
         else:
