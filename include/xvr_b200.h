@@ -120,8 +120,9 @@ int xvr_sobel_bwd(const float* gout, int B, int H, int W, float* gx /* (B,1,H,W)
  * once per HU volume (independent of the multiplier; workspace = 4 ints, stats = 4 floats, both DEVICE);
  * xvr_hu_to_density is the one-pass piecewise map, shifted and scaled to [0,1]. */
 int xvr_hu_stats(const float* hu, long long n, float air, float bone, int* workspace, float* stats, void* stream);
-int xvr_hu_to_density(const float* hu, long long n, float air, float bone, float multiplier, const float* stats,
-                      float* out, void* stream);
+int xvr_hu_to_density(const float* hu, long long n, float air, float bone, float multiplier,
+                      const float* multiplier_dev /* NULL, or DEVICE float overriding `multiplier` */,
+                      const float* stats, float* out, void* stream);
 
 /* out[r] = sum_n in[r,n], fixed summation tree */
 int xvr_reduce_rows(const float* in, int rows, int N, float* out, void* stream);

@@ -19,6 +19,8 @@ ap.add_argument("--n-vols", type=int, default=8)
 ap.add_argument("--height", type=int, default=128)
 ap.add_argument("--batch", type=int, default=116)
 ap.add_argument("--labels", action="store_true")
+ap.add_argument("--graph", action="store_true", help="replay the iteration as CUDA graphs (TrainStep(use_cuda_graph=True))")
+ap.add_argument("--log-every", type=int, default=4)
 args = ap.parse_args()
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
@@ -42,14 +44,20 @@ for seed in range(args.n_vols):
 torch.manual_seed(0)
 model = PoseRegressor("resnet18", "quaternion_adjugate", "ZXY", height=args.height, norm_layer="groupnorm").to(dev)
 step = TrainStep(drr, model, volumes, bench.POSE_RANGES, XrayTransforms(args.height), bench.SDD, batch_size=args.batch,
-                 n_grad_accum_itrs=4, n_warmup_itrs=8)
-for i in range(args.warmup):
-    log = step.step(i)
+                 n_grad_accum_itrs=4, n_warmup_itrs=8, use_cuda_graph=args.graph,
+                 log_every=args.log_every if args.graph else 1)
+i0 = 0
+for i0 in range(args.warmup):
+    log = step.step(i0)
+i0 = args.warmup
+while args.graph and (len(step._graphs) < args.n_vols or step._opt_graph is None):  # capture every subject's graph
+    log = step.step(i0)
+    i0 += 1
 torch.cuda.synchronize()
 if world > 1:
     dist.barrier()
 t0 = time.time()
-for i in range(args.warmup, args.warmup + args.steps):
+for i in range(i0, i0 + args.steps):
     log = step.step(i)
 torch.cuda.synchronize()
 if world > 1:
@@ -57,8 +65,15 @@ if world > 1:
 dt = time.time() - t0
 if rank == 0:
     print(json.dumps({"workload": f"xvr train step: {args.n_vols} x {args.vol}^3 volumes, batch {args.batch} sharded over {world} GPU(s), "
-                      f"{args.height}^2 DRRs, resnet18+GroupNorm, 2 renders/step, labels={args.labels}",
+                      f"{args.height}^2 DRRs, resnet18+GroupNorm, 2 renders/step, labels={args.labels}, cuda_graph={args.graph}",
                       "n_gpus": world, "ms_per_step": 1e3 * dt / args.steps, "steps_per_s": args.steps / dt,
                       "drrs_per_s": 2 * args.batch * args.steps / dt, "last_log": log}))
 if world > 1:
+    if args.graph:
+        # captured graphs hold NCCL kernels of this communicator: tearing the communicator down under them hangs
+        # (observed with NCCL 2.28.9) -- leave it to process exit
+        sys.stdout.flush()
+        dist.barrier()
+        torch.cuda.synchronize()
+        os._exit(0)
     dist.destroy_process_group()

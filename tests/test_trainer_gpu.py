@@ -88,3 +88,32 @@ def test_dice_and_agc_semantics(cuda):
     p.grad = torch.full_like(p, 10.0)
     adaptive_clip_grad_([p], clip_factor=0.01, eps=1e-3)
     assert torch.allclose(p.grad.norm(dim=1), torch.full((4,), 0.01 * 8**0.5, device=cuda), rtol=1e-4)
+
+
+@pytest.mark.parametrize("wide,labels", [(False, False), (True, False), (False, True)])
+def test_graph_mode_matches_eager(cuda, wide, labels):
+    """The CUDA-graph iteration keeps dropped samples in the batch with weight 0 instead of indexing them away
+    (static shapes); it must train like the eager, reference-shaped iteration: same kept fraction, same losses,
+    same parameter trajectory (up to the round-off of a different batch size inside cuDNN/cuBLAS)."""
+    ranges = dict(POSE_RANGES)
+    if wide:  # some poses lose the volume -> keep < 1
+        ranges.update(txmin=-450.0, txmax=450.0, tzmin=-450.0, tzmax=450.0)
+    logs, final, init = {}, {}, None
+    for graph in (False, True):
+        drr, model, volumes = _setup(cuda, labels=labels)
+        init = torch.cat([p.detach().flatten().clone() for p in model.parameters()])
+        step = TrainStep(drr, model, volumes, ranges, XrayTransforms(32), SDD, batch_size=8, n_grad_accum_itrs=2,
+                         n_warmup_itrs=2, lr=1e-3, use_cuda_graph=graph)
+        logs[graph] = [step.step(i) for i in range(6)]
+        final[graph] = torch.cat([p.detach().flatten() for p in model.parameters()])
+    kept = [log["kept"] for log in logs[False]]
+    if wide:
+        assert min(kept) < 1.0 and max(kept) > 0.0, kept
+    for i, (a, b) in enumerate(zip(logs[False], logs[True])):
+        assert a["kept"] == pytest.approx(b["kept"], abs=1e-6), (i, a, b)
+        assert a["lr"] == pytest.approx(b["lr"], rel=1e-6), (i, a, b)
+        for k in ("loss", "mncc", "dgeo", "dice"):
+            assert a[k] == pytest.approx(b[k], rel=5e-3 if i < 2 else 5e-2, abs=1e-3), (i, k, a, b)
+    da, db = final[False] - init, final[True] - init
+    assert da.norm() > 0
+    assert (torch.dot(da, db) / (da.norm() * db.norm())).item() > 0.97

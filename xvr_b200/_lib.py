@@ -42,7 +42,7 @@ _SIGNATURES = {
     "xvr_sobel_fwd": ([P, c_int, c_int, c_int, P, P], c_int),
     "xvr_sobel_bwd": ([P, c_int, c_int, c_int, P, P], c_int),
     "xvr_hu_stats": ([P, ctypes.c_longlong, c_float, c_float, P, P, P], c_int),
-    "xvr_hu_to_density": ([P, ctypes.c_longlong, c_float, c_float, c_float, P, P, P], c_int),
+    "xvr_hu_to_density": ([P, ctypes.c_longlong, c_float, c_float, c_float, P, P, P, P], c_int),
     "xvr_reduce_rows": ([P, c_int, c_int, P, P], c_int),
     "xvr_siddon_rays_fwd": (
         [P, c_int, c_int, c_int, P, c_int, P, P, P, c_int, c_int, c_float, c_float, c_int, c_int, c_int, c_int, P, P,

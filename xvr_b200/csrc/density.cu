@@ -59,8 +59,9 @@ __global__ void hu_stats_finish_kernel(const int* __restrict__ keys, float* __re
 
 // density = (f(h) - lo) / (hi - lo),  f = soft_min (air), h (soft tissue), m*h (bone)
 __global__ void __launch_bounds__(256) hu_map_kernel(const float* __restrict__ hu, int64_t n, float air, float bone,
-                                                     float m, const float* __restrict__ stats,
-                                                     float* __restrict__ out) {
+                                                     float m, const float* __restrict__ m_dev,
+                                                     const float* __restrict__ stats, float* __restrict__ out) {
+  if (m_dev) m = __ldg(m_dev);  // multiplier from device memory: the launch can sit in a CUDA graph and still vary
   const float smin = stats[0], smax = stats[1], bmin = stats[2], bmax = stats[3];
   const bool has_bone = bmax > -INFINITY;
   float lo = smin, hi = smax;
@@ -99,13 +100,15 @@ extern "C" int xvr_hu_stats(const float* hu, long long n, float air, float bone,
   return check_launch("xvr_hu_stats/finish");
 }
 
+// multiplier_dev: NULL, or a DEVICE float that overrides `multiplier` (read by the kernel, so a captured launch
+// follows the value of the moment)
 extern "C" int xvr_hu_to_density(const float* hu, long long n, float air, float bone, float multiplier,
-                                 const float* stats, float* out, void* stream) {
+                                 const float* multiplier_dev, const float* stats, float* out, void* stream) {
   if (!hu || !stats || !out || n <= 0) {
     set_last_error("xvr_hu_to_density: invalid argument");
     return XVR_ERR_INVALID;
   }
   const int grid = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
-  hu_map_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(hu, n, air, bone, multiplier, stats, out);
+  hu_map_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(hu, n, air, bone, multiplier, multiplier_dev, stats, out);
   return check_launch("xvr_hu_to_density");
 }

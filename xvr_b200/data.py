@@ -53,34 +53,36 @@ class Subject:
 
 
 class _HuStats:
-    """{min soft, max soft, min bone, max bone} of the last HU volume seen (they do not depend on the multiplier,
-    and training calls transform_hu_to_density on the same volume every step)."""
+    """{min soft, max soft, min bone, max bone} per HU volume (they do not depend on the multiplier, and training
+    calls transform_hu_to_density on the same few volumes every step): one reduction per volume object and
+    version, kept while the volume is alive."""
 
     def __init__(self):
-        self.src = None
-        self.version = None
-        self.stats = None
+        self.cache = {}  # id(volume) -> (weakref to the volume, version, stats); entries die with their volume
 
     def get(self, volume):
-        if self.src is None or self.src() is not volume or self.version != volume._version:
+        key = id(volume)
+        hit = self.cache.get(key)
+        if hit is None or hit[0]() is not volume or hit[1] != volume._version:
             from ._lib import call, ptr, stream  # noqa: PLC0415
 
-            self.stats = torch.empty(4, device=volume.device, dtype=torch.float32)
+            stats = torch.empty(4, device=volume.device, dtype=torch.float32)
             work = torch.empty(4, device=volume.device, dtype=torch.int32)
-            call("xvr_hu_stats", ptr(volume), volume.numel(), conv.HU_AIR, conv.HU_BONE, ptr(work), ptr(self.stats),
-                 stream())
-            self.src, self.version = weakref.ref(volume), volume._version
-        return self.stats
+            call("xvr_hu_stats", ptr(volume), volume.numel(), conv.HU_AIR, conv.HU_BONE, ptr(work), ptr(stats), stream())
+            hit = (weakref.ref(volume, lambda _, k=key, c=self.cache: c.pop(k, None)), volume._version, stats)
+            self.cache[key] = hit
+        return hit[2]
 
 
 _hu_stats = _HuStats()
 
 
-def transform_hu_to_density(volume, bone_attenuation_multiplier):
+def transform_hu_to_density(volume, bone_attenuation_multiplier, out=None):
     """Piecewise HU -> density map, shifted and scaled to [0,1].
 
     air (HU <= -800) takes the minimum soft-tissue value, soft tissue (-800, 350] is kept, bone (> 350) is
-    multiplied by ``bone_attenuation_multiplier``.  CUDA volumes (the per-step call of the training loop) go
+    multiplied by ``bone_attenuation_multiplier`` (a float, or a 1-element CUDA tensor that the kernel reads at run
+    time -- what a CUDA-graph-captured training step needs).  ``out`` optionally receives the result.  CUDA volumes (the per-step call of the training loop) go
     through the one-pass kernel of csrc/density.cu; CPU volumes (``read`` at set-up time, before ``.to(device)``)
     are mapped with tensor ops.
     """
@@ -88,9 +90,18 @@ def transform_hu_to_density(volume, bone_attenuation_multiplier):
         from ._lib import call, ptr, stream  # noqa: PLC0415
 
         vol = volume if (volume.dtype == torch.float32 and volume.is_contiguous()) else volume.float().contiguous()
-        out = torch.empty_like(vol)
-        call("xvr_hu_to_density", ptr(vol), vol.numel(), conv.HU_AIR, conv.HU_BONE, float(bone_attenuation_multiplier),
-             ptr(_hu_stats.get(vol)), ptr(out), stream())
+        if out is None:
+            out = torch.empty_like(vol)
+        elif out.shape != vol.shape or out.dtype != torch.float32 or not out.is_contiguous() or out.device != vol.device:
+            raise ValueError("out must be a contiguous float32 tensor of the volume's shape on the volume's device")
+        m_dev = None
+        if torch.is_tensor(bone_attenuation_multiplier):
+            m_dev = bone_attenuation_multiplier
+            if not m_dev.is_cuda or m_dev.dtype != torch.float32 or m_dev.numel() != 1:
+                raise ValueError("a tensor multiplier must be a 1-element float32 CUDA tensor")
+        call("xvr_hu_to_density", ptr(vol), vol.numel(), conv.HU_AIR, conv.HU_BONE,
+             0.0 if m_dev is not None else float(bone_attenuation_multiplier), ptr(m_dev), ptr(_hu_stats.get(vol)),
+             ptr(out), stream())
         return out
     volume = volume.to(torch.float32)
     soft = (volume > conv.HU_AIR) & (volume <= conv.HU_BONE)

@@ -161,17 +161,28 @@ def rotation_6d_to_matrix(d6):
     return torch.stack((b1, b2, torch.cross(b1, b2, dim=-1)), -2)
 
 
+# Index tables of the symmetric 4x4 <-> 10-vector maps, cached per device: building them on the fly would copy a
+# CPU index tensor to the GPU on every call, which a CUDA-graph capture (the graphed training step) forbids.
+_SYM4_GATHER = (0, 1, 2, 3, 1, 4, 5, 6, 2, 5, 7, 8, 3, 6, 8, 9)  # flat 4x4 position -> component of the 10-vector
+_TRIU4_GATHER = (0, 1, 2, 3, 5, 6, 7, 10, 11, 15)                # component -> flat 4x4 position (row-major triu)
+_index_cache = {}
+
+
+def _const_index(name, values, device):
+    key = (name, device)
+    if key not in _index_cache:
+        _index_cache[key] = torch.tensor(values, dtype=torch.long, device=device)
+    return _index_cache[key]
+
+
 def _sym4(v):
-    i, j = torch.triu_indices(4, 4)
-    A = torch.zeros(v.shape[:-1] + (4, 4), dtype=v.dtype, device=v.device)
-    A[..., i, j] = v
-    A[..., j, i] = v
-    return A
+    """10-vector (row-major upper triangle) -> symmetric 4x4."""
+    return v.index_select(-1, _const_index("sym4", _SYM4_GATHER, v.device)).reshape(v.shape[:-1] + (4, 4))
 
 
 def _triu4(A):
-    i, j = torch.triu_indices(4, 4)
-    return A[..., i, j]
+    """4x4 -> its row-major upper triangle as a 10-vector."""
+    return A.reshape(A.shape[:-2] + (16,)).index_select(-1, _const_index("triu4", _TRIU4_GATHER, A.device))
 
 
 def quaternion_adjugate_to_quaternion(v):

@@ -57,6 +57,11 @@ class _VolumeTexture:
             self.src, self.version = weakref.ref(volume), volume._version
         return self.handle
 
+    def invalidate(self):
+        """Forget what was uploaded last: the next ``get`` re-uploads.  Needed when the source tensor is rewritten
+        through its raw pointer (no version bump), e.g. the static density buffer of a graph-captured step."""
+        self.src = None
+
     def __deepcopy__(self, memo):
         return _VolumeTexture()  # device resources are per-instance: the copy re-creates its own lazily
 

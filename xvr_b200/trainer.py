@@ -88,9 +88,11 @@ class PoseRegressionLoss(torch.nn.Module):
         dice = self.diceloss(mask, pred_mask)
         rgeo, tgeo, dgeo = self.geodesic(pose, pred_pose)
         loss = self.weight_ncc * (1 - mncc) + self.weight_dice * dice + self.weight_geo * dgeo
-        mvc = self.multiview_consistency(pose, pred_pose)
         if self.weight_mvc > 0:
+            mvc = self.multiview_consistency(pose, pred_pose)
             loss = loss + self.weight_mvc * mvc.mean()
+        else:  # the reference evaluates it for its log only (B(B-1)/2 pose pairs); skipped when it carries no weight
+            mvc = loss.new_zeros(1)
         return loss, mncc, dgeo, rgeo, tgeo, dice, mvc
 
     def multiview_consistency(self, true_pose, pred_pose):
@@ -161,7 +163,8 @@ class TrainStep:
 
     def __init__(self, drr, model, volumes, pose_distribution, transforms, sdd, batch_size=116, lr=2e-4,
                  n_total_itrs=1_000_000, n_warmup_itrs=1_000, n_grad_accum_itrs=4, weight_ncc=1.0, weight_geo=1e-2,
-                 weight_dice=1.0, weight_mvc=0.0, seed=0, standardize_global=True, disable_scheduler=False):
+                 weight_dice=1.0, weight_mvc=0.0, seed=0, standardize_global=True, disable_scheduler=False,
+                 use_cuda_graph=False, log_every=1):
         self.rank, self.world = _world()
         self.drr, self.model, self.volumes, self.transforms = drr, model, volumes, transforms
         self.pose_distribution = dict(pose_distribution)
@@ -180,6 +183,11 @@ class TrainStep:
         self.pose_rng = torch.Generator().manual_seed(seed * 9973 + 1 + self.rank)
         self.standardize_global = standardize_global and self.world > 1
         self.device = next(model.parameters()).device
+        self.use_cuda_graph = bool(use_cuda_graph)
+        self.log_every = max(1, int(log_every))
+        self._schedule = None if disable_scheduler else self.scheduler._factor
+        if self.use_cuda_graph:
+            self._init_graph_mode(lr)
 
     # ------------------------------------------------------------------ pieces
     def _standardize(self, x):
@@ -208,6 +216,8 @@ class TrainStep:
 
     # ------------------------------------------------------------------ the iteration
     def step(self, itr):
+        if self.use_cuda_graph:
+            return self._step_graphed(itr)
         dev = self.device
         subject = int(torch.randint(len(self.volumes), (1,), generator=self.shared_rng))
         contrast = float(torch.empty(1).uniform_(1.0, 10.0, generator=self.shared_rng))
@@ -250,3 +260,169 @@ class TrainStep:
             self.optimizer.zero_grad()
         log["lr"] = self.scheduler.get_last_lr()[0]
         return log
+
+    # ------------------------------------------------------------------ the iteration as CUDA graphs
+    # The eager iteration above costs ~20 ms of host time (a ResNet forward/backward, two renders, ~10^3 small
+    # launches and five host round trips), more than its GPU time -- and at 8 ranks the GPU share shrinks 8x while
+    # the host share does not.  Graph mode replays one captured graph per subject for the iteration and one for the
+    # optimiser step.  What makes it capturable:
+    #   * static shapes: instead of dropping the samples that miss the volume (img[keep], trainer.py:202-204) they
+    #     stay in the batch with weight 0.  Exact, not an approximation: the network normalises per sample
+    #     (GroupNorm), the losses are per sample, the batch-global min/max of Standardize is taken over the kept
+    #     samples only, and the mean divides by the kept count;
+    #   * no host reads: kept count and log values stay on the device and are fetched every ``log_every`` steps;
+    #   * run-time scalars in device memory: pose batch, contrast (density kernel reads it), learning rate
+    #     (Adam(capturable=True) with a tensor lr, set from the same WarmupCosineSchedule formula);
+    #   * the density goes to a static buffer and its texture upload is part of the captured work;
+    #   * collectives (kept count, log sums, min/max, gradient all-reduce) are captured NCCL calls.
+    def _standardize_masked(self, x, keep):
+        """XrayTransforms whose batch-global min/max run over the KEPT samples only (the reference standardises
+        img[keep]); with nothing kept anywhere the range falls back to [0, 1] and every weight is 0 anyway."""
+        sel = keep.view(-1, 1, 1, 1)
+        lo = torch.where(sel, x.detach(), torch.full_like(x, float("inf"))).min()
+        hi = torch.where(sel, x.detach(), torch.full_like(x, float("-inf"))).max()
+        if self.standardize_global:
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        lo = torch.where(torch.isfinite(lo), lo, torch.zeros_like(lo))
+        hi = torch.where(torch.isfinite(hi), hi, torch.ones_like(hi))
+        t = self.transforms
+        x = (x - lo) / (hi - lo + t.standardize.eps)
+        if t.equalize is not None:
+            x = t.equalize(x)
+        if tuple(x.shape[-2:]) != t.size:
+            x = torch.nn.functional.interpolate(x, size=t.size, mode="bilinear", align_corners=False, antialias=True)
+        return (x - t.mean) / t.std
+
+    def _device_iteration(self, subject):
+        vol, seg, affinv, offset = self.volumes[subject]
+        pose = convert(self._rot, self._xyz, parameterization="euler_angles", convention="ZXY", degrees=True)
+        pose = pose.compose(offset)
+        density = transform_hu_to_density(vol, self._contrast, out=self._density_buffer(vol))
+        if hasattr(self.drr.renderer, "_texture"):
+            self.drr.renderer._texture.invalidate()  # the buffer is rewritten through its raw pointer: upload again
+        with torch.no_grad():
+            img, mask, keep = render_samples(self.drr, density, seg, affinv, pose)
+        w = keep.to(torch.float32)
+        kept = w.sum().reshape(1)
+        if self.world > 1:
+            dist.all_reduce(kept, op=dist.ReduceOp.SUM)
+        x = self._standardize_masked(img, keep)
+        pred_pose = self.model(x)
+        pred_img, pred_mask, _ = render_samples(self.drr, density, seg, affinv, pred_pose)
+        x_pred = self._standardize_masked(pred_img, keep)
+        loss, mncc, dgeo, rgeo, tgeo, dice, _ = self.lossfn(x, mask, pose, x_pred, pred_mask, pred_pose)
+        denom = kept.clamp_min(1.0)
+        ((loss * w).sum() / denom / self.n_grad_accum_itrs).backward()
+        with torch.no_grad():
+            sums = torch.stack([(v.detach() * w).sum() for v in (loss, mncc, dgeo, rgeo, tgeo, dice)])
+            if self.world > 1:
+                dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+            self._log.copy_(torch.cat([sums / denom, kept / self.batch_size]))
+
+    def _device_optimizer_step(self):
+        self._allreduce_grads()
+        adaptive_clip_grad_(self.model.parameters())
+        self.optimizer.step()
+        self.optimizer.zero_grad(set_to_none=False)
+
+    def _density_buffer(self, vol):
+        key = tuple(vol.shape)
+        if key not in self._density:
+            self._density[key] = torch.empty(key, device=vol.device, dtype=torch.float32)
+        return self._density[key]
+
+    def _init_graph_mode(self, lr):
+        if self.lossfn.weight_mvc > 0:
+            raise NotImplementedError("use_cuda_graph: the multiview-consistency term pairs samples across the batch "
+                                      "and is not masked; train with weight_mvc = 0 (the reference default)")
+        dev = self.device
+        B = self.local_batch
+        self._rot = torch.zeros(B, 3, device=dev)
+        self._xyz = torch.zeros(B, 3, device=dev)
+        self._contrast = torch.ones(1, device=dev)
+        self._log = torch.zeros(7, device=dev)
+        self._density = {}
+        self._graphs = {}
+        self._opt_graph = None
+        self._pool = None
+        self._opt_steps = 0
+        self._base_lr = lr
+        self._lr = torch.tensor(lr * self._lr_factor(0), device=dev, dtype=torch.float32)
+        self.optimizer = torch.optim.Adam(self.model.parameters(), lr=self._lr, capturable=True)
+        for p in self.model.parameters():  # static .grad tensors shared by every graph
+            p.grad = torch.zeros_like(p)
+        # pinned staging ring for the per-step pose batch: the host may run several steps ahead of the device
+        self._stage = [(torch.empty(B, 3).pin_memory(), torch.empty(B, 3).pin_memory(), torch.cuda.Event())
+                       for _ in range(8)]
+        self._stage_used = [False] * 8
+        self._last_log = {}
+
+    def _lr_factor(self, opt_step):
+        return 1.0 if self._schedule is None else self._schedule(opt_step)
+
+    def _capture(self, fn, *args):
+        """Warm up on a side stream (lazy initialisation, allocator pools, texture creation), then capture."""
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            fn(*args)
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, pool=self._pool):
+            fn(*args)
+        if self._pool is None:
+            self._pool = graph.pool()
+        return graph
+
+    def _step_graphed(self, itr):
+        subject = int(torch.randint(len(self.volumes), (1,), generator=self.shared_rng))
+        contrast = float(torch.empty(1).uniform_(1.0, 10.0, generator=self.shared_rng))
+        rot, xyz = random_pose_params(**self.pose_distribution, batch_size=self.local_batch, generator=self.pose_rng)
+        slot = itr % len(self._stage)
+        rot_h, xyz_h, ev = self._stage[slot]
+        if self._stage_used[slot]:
+            ev.synchronize()  # the copies that last read these pinned buffers have run
+        rot_h.copy_(rot)
+        xyz_h.copy_(xyz)
+        self._rot.copy_(rot_h, non_blocking=True)
+        self._xyz.copy_(xyz_h, non_blocking=True)
+        ev.record()
+        self._stage_used[slot] = True
+        self._contrast.fill_(contrast)
+
+        if subject not in self._graphs:
+            # warm-up + capture run the iteration twice without it counting: keep the accumulated gradients
+            saved = [p.grad.clone() for p in self.model.parameters()]
+            self._graphs[subject] = self._capture(self._device_iteration, subject)
+            for p, g in zip(self.model.parameters(), saved):
+                p.grad.copy_(g)
+        self._graphs[subject].replay()
+
+        if (itr + 1) % self.n_grad_accum_itrs == 0 or (itr + 1) == self.n_total_itrs:
+            if self._opt_graph is None:
+                self._opt_graph = self._capture_optimizer()
+            else:
+                self._opt_graph.replay()
+            self._opt_steps += 1
+            self._lr.fill_(self._base_lr * self._lr_factor(self._opt_steps))
+        if (itr + 1) % self.log_every == 0:
+            vals = self._log.tolist()  # the only host round trip, every log_every iterations
+            self._last_log = dict(zip(("loss", "mncc", "dgeo", "rgeo", "tgeo", "dice", "kept"), vals))
+        log = dict(self._last_log)
+        log["lr"] = self._base_lr * self._lr_factor(self._opt_steps)
+        return log
+
+    def _capture_optimizer(self):
+        """The first optimiser step runs eagerly on a side stream (Adam's lazy state initialisation must not be
+        captured) and counts; the graph captured right after it serves every later step.  Capturing executes
+        nothing, but the eager warm-up inside ``_capture`` would: so capture by hand here."""
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            self._device_optimizer_step()
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, pool=self._pool):
+            self._device_optimizer_step()
+        return graph
