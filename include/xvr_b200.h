@@ -66,9 +66,11 @@ int xvr_trilinear_drr_fwd(const float* volume, const void* voltex, int D0, int D
                           const float* cam2world, const float* det9, int B, int det_h, int det_w, int n_points,
                           int step_mode, float eps, int lane_w_log2, int cta_w_log2, float* out, float* jac,
                           void* stream);
-/* gG (B,3,4) = dL/d cam2vox from the saved Jacobian and gout (B,1,H*W) */
+/* gG (B,3,4) = dL/d cam2vox from the saved Jacobian and gout (B,1,H*W).  workspace: NULL, or
+ * 12 * B * xvr_drr_jac_bwd_slices(B, H*W) floats so that small batches spread each pose over several CTAs */
+int xvr_drr_jac_bwd_slices(int B, int N);
 int xvr_drr_jac_bwd(const float* jac, const float* gout, const float* det9, int B, int det_h, int det_w, float* gG,
-                    void* stream);
+                    float* workspace, void* stream);
 
 /* dL/dvolume of xvr_trilinear_drr_fwd = the `grad_input` half of grid_sampler_3d_backward (fastAtomicAdd scatter,
  * ATen/native/cuda/GridSampler.cuh:263-280), here in gather form: one owner thread per voxel, no atomics,
@@ -114,6 +116,25 @@ int xvr_ncc_bwd(const float* x1, const float* x2, const float* coef, int which, 
                 int H, int W, int patch, float weight, int accumulate, float* grad, void* stream);
 int xvr_sobel_fwd(const float* x, int B, int H, int W, float* out /* (B,2,H,W) */, void* stream);
 int xvr_sobel_bwd(const float* gout, int B, int H, int W, float* gx /* (B,1,H,W) */, void* stream);
+
+/* ---- The scalar ends of one registration iteration, one launch each (/root/reference/src/xvr/registrar/base.py:245-278).
+ * xvr_euler_camera_*: convert(rot, xyz, "euler_angles", convention) -> reorient.compose(pose) -> affine inverse,
+ *   i.e. the camera matrices the fused renderer consumes, and the matching backward.  rot, xyz (B,3) DEVICE;
+ *   axes HOST int[3] (0/1/2 = X/Y/Z of the convention string); reorient16, affinv16 HOST row-major 4x4;
+ *   cam2world, cam2vox, gcam2vox (B,3,4); grot, gxyz (B,3).
+ * xvr_reg_update: torch.optim.Adam(maximize=True) on (rot, xyz) + ReduceLROnPlateau(mode="max") + the stopping rule
+ *   and trajectory row of run_test_time_optimization.  state8 DEVICE double[8] = {Adam step, best, num_bad, smallest
+ *   lr seen, n_plateaus, active, lr_rot, lr_xyz}; hyper9 HOST double[9] = {beta1, beta2, Adam eps, factor, patience,
+ *   threshold, min_lr, scheduler eps, max_n_plateaus}; log_rows (max_rows, 1 + n_rot + 3 + 2), log_count DEVICE float. */
+int xvr_euler_camera_fwd(const float* rot, const float* xyz, int B, const int* axes, int rotated_frame,
+                         const float* reorient16, const float* affinv16, float* cam2world, float* cam2vox,
+                         void* stream);
+int xvr_euler_camera_bwd(const float* rot, const float* xyz, int B, const int* axes, int rotated_frame,
+                         const float* reorient16, const float* affinv16, const float* gcam2vox, float* grot,
+                         float* gxyz, void* stream);
+int xvr_reg_update(float* rot, float* xyz, const float* grot, const float* gxyz, int n_rot, float* m_rot, float* v_rot,
+                   float* m_xyz, float* v_xyz, double* state8, const float* loss, float* log_rows, float* log_count,
+                   int max_rows, const double* hyper9, void* stream);
 
 /* ---- HU -> density = diffdrr.data.transform_hu_to_density, called every step at
  * /root/reference/src/xvr/model/trainer.py:196-197.  xvr_hu_stats reduces {min soft, max soft, min bone, max bone}

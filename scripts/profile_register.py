@@ -8,9 +8,13 @@ rot0 = torch.tensor([[0.20, -0.10, 0.05]], device="cuda"); xyz0 = torch.tensor([
 with torch.no_grad():
     gt = drr(xvr_b200.convert(rot0, xyz0, parameterization="euler_angles", convention="ZXY"))
 init = xvr_b200.convert(rot0 + 0.05, xyz0 + 8.0, parameterization="euler_angles", convention="ZXY")
-reg = Registrar(drr, scales="1", n_itrs="20", max_n_plateaus=10**6, use_cuda_graph=False, poll_every=50)
+graph = len(sys.argv) > 1 and sys.argv[1] == "graph"
+reg = Registrar(drr, scales="1", n_itrs="20", max_n_plateaus=10**6, use_cuda_graph=graph, poll_every=50)
 reg.run(gt, init)
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     reg.run(gt, init)
     torch.cuda.synchronize()
-print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=25, max_name_column_width=70))
+ka = prof.key_averages()
+print(ka.table(sort_by="cuda_time_total", row_limit=30, max_name_column_width=70))
+kern = [e for e in ka if e.device_type.name == "CUDA"]
+print("GPU kernels per iteration:", sum(e.count for e in kern) / 20, " GPU time per iteration (us):", sum(e.device_time_total for e in kern) / 20)

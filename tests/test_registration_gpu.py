@@ -72,3 +72,45 @@ def test_trajectory_matches_the_reference_loop_on_the_oracle(cuda):
     assert (final[:3] - rot.detach().cpu().flatten()).abs().max().item() < 2e-3
     assert (final[3:] - xyz.detach().cpu().flatten()).abs().max().item() < 0.2
     _ = rel_l2
+
+
+@pytest.mark.parametrize("convention", ["ZXY", "XYZ", "YZX"])
+def test_one_launch_euler_camera_matches_the_tensor_chain(cuda, convention, monkeypatch):
+    """DRR.forward(rot, xyz, parameterization="euler_angles") builds the camera matrices in one launch
+    (csrc/regstep.cu); image and pose gradients must equal the convert -> compose -> affine-inverse tensor chain."""
+    drr = make_drr(48, 32)
+    rot = torch.tensor([[0.30, -0.20, 0.10], [-0.15, 0.25, 0.05]], device=cuda)
+    xyz = torch.tensor([[12.0, 790.0, -8.0], [-20.0, 860.0, 15.0]], device=cuda)
+    w = torch.rand(2, 1, 32, 32, generator=torch.Generator().manual_seed(2)).to(cuda)
+    out = {}
+    for fused in ("1", "0"):
+        monkeypatch.setenv("XVR_B200_FUSED_POSE", fused)
+        r, x = rot.clone().requires_grad_(), xyz.clone().requires_grad_()
+        img = drr(r, x, parameterization="euler_angles", convention=convention)
+        (img * w).sum().backward()
+        out[fused] = (img.detach(), r.grad, x.grad)
+    assert rel_l2(out["1"][0], out["0"][0]) < 1e-5
+    assert rel_l2(out["1"][1], out["0"][1]) < 2e-3 and rel_l2(out["1"][2], out["0"][2]) < 2e-3
+    # degrees=True goes through the same kernel
+    monkeypatch.setenv("XVR_B200_FUSED_POSE", "1")
+    img_deg = drr(torch.rad2deg(rot), xyz, parameterization="euler_angles", convention=convention, degrees=True)
+    assert rel_l2(img_deg, out["1"][0]) < 1e-5
+
+
+def test_fused_update_matches_tensor_op_update(cuda):
+    """xvr_reg_update (Adam + plateau scheduler + stopping rule + log row in one launch) against the tensor-op
+    implementations that tests/test_cpu_registrar.py pins to torch.optim: same trajectory, same stop iteration."""
+    res = []
+    for fused in (True, False):
+        drr, gt, init, *_ = _problem(cuda)
+        pose, info = Registrar(drr, scales="1", n_itrs="120", patience=3, max_n_plateaus=2, use_cuda_graph=True,
+                               fused_update=fused).run(gt, init)
+        res.append((pose.matrix.clone(), info))
+    a, b = res[0][1], res[1][1]
+    assert a["n_itrs"] == b["n_itrs"] and a["n_itrs"][0] < 120  # the stopping rule fired, at the same iteration
+    # same arithmetic, different association (fp32 products folded differently): the two optimisations drift apart
+    # by ~1e-4 in similarity over tens of iterations, far below anything the plateau logic reacts to
+    assert torch.allclose(torch.tensor(a["nccs"]), torch.tensor(b["nccs"]), atol=1e-3)
+    assert torch.allclose(torch.tensor(a["alphas"]), torch.tensor(b["alphas"]), rtol=1e-6, atol=0)
+    assert torch.allclose(torch.tensor(a["params"]), torch.tensor(b["params"]), rtol=2e-3, atol=2e-2)
+    assert torch.allclose(res[0][0], res[1][0], atol=2e-2)

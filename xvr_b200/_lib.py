@@ -30,7 +30,8 @@ _SIGNATURES = {
     "xvr_trilinear_drr_fwd": (
         [P, P, c_int, c_int, c_int, P, P, ctypes.POINTER(c_float), c_int, c_int, c_int, c_int, c_int, c_float, c_int,
          c_int, P, P, P], c_int),
-    "xvr_drr_jac_bwd": ([P, P, ctypes.POINTER(c_float), c_int, c_int, c_int, P, P], c_int),
+    "xvr_drr_jac_bwd": ([P, P, ctypes.POINTER(c_float), c_int, c_int, c_int, P, P, P], c_int),
+    "xvr_drr_jac_bwd_slices": ([c_int, c_int], c_int),
     "xvr_trilinear_drr_bwd_volume": (
         [P, P, P, ctypes.POINTER(c_float), c_int, c_int, c_int, c_int, c_int, c_float, P, c_int, c_int, c_int, P, P,
          c_int, P], c_int),
@@ -44,6 +45,11 @@ _SIGNATURES = {
     "xvr_hu_stats": ([P, ctypes.c_longlong, c_float, c_float, P, P, P], c_int),
     "xvr_hu_to_density": ([P, ctypes.c_longlong, c_float, c_float, c_float, P, P, P, P], c_int),
     "xvr_reduce_rows": ([P, c_int, c_int, P, P], c_int),
+    "xvr_euler_camera_fwd": ([P, P, c_int, ctypes.POINTER(c_int), c_int, ctypes.POINTER(c_float),
+                              ctypes.POINTER(c_float), P, P, P], c_int),
+    "xvr_euler_camera_bwd": ([P, P, c_int, ctypes.POINTER(c_int), c_int, ctypes.POINTER(c_float),
+                              ctypes.POINTER(c_float), P, P, P, P], c_int),
+    "xvr_reg_update": ([P, P, P, P, c_int, P, P, P, P, P, P, P, P, c_int, ctypes.POINTER(ctypes.c_double), P], c_int),
     "xvr_siddon_rays_fwd": (
         [P, c_int, c_int, c_int, P, c_int, P, P, P, c_int, c_int, c_float, c_float, c_int, c_int, c_int, c_int, P, P,
          P], c_int),

@@ -336,17 +336,21 @@ __global__ void __launch_bounds__(1024) reduce_rows_kernel(const float* __restri
 }
 
 // Fused-path backward: dL/dG (B,3,4) from the saved per-ray Jacobian.  t_r = G [c_r; 1], s = G[:,3]  =>
-// dL/dG[:, :3] = sum_r g_r J_t,r (x) c_r,  dL/dG[:, 3] = sum_r g_r (J_t,r + J_s,r).  One CTA per pose, fixed tree.
+// dL/dG[:, :3] = sum_r g_r J_t,r (x) c_r,  dL/dG[:, 3] = sum_r g_r (J_t,r + J_s,r).  gridDim.y CTAs share a pose
+// (each reduces a contiguous slice of its rays with a fixed tree and writes 12 partial sums); a second pass adds the
+// slices in order, so the result is deterministic for a given launch shape.
 __global__ void __launch_bounds__(1024)
 drr_jac_bwd_kernel(const float* __restrict__ jac, const float* __restrict__ gout, int N, DetectorGeom geom,
-                   float* __restrict__ gG) {
+                   float* __restrict__ partial) {
   __shared__ float part[32][12];
-  const int b = blockIdx.x;
+  const int b = blockIdx.x, slice = blockIdx.y, S = gridDim.y;
+  const int per = (N + S - 1) / S;
+  const int n0 = slice * per, n1 = min(N, n0 + per);
   float acc[12];
 #pragma unroll
   for (int k = 0; k < 12; ++k) acc[k] = 0.f;
   const float* j = jac + (int64_t)b * 7 * N;
-  for (int n = threadIdx.x; n < N; n += 1024) {
+  for (int n = n0 + threadIdx.x; n < n1; n += 1024) {
     const float g = __ldg(gout + (int64_t)b * N + n);
     float c[3];
     camera_point(geom, n, c);
@@ -370,9 +374,18 @@ drr_jac_bwd_kernel(const float* __restrict__ jac, const float* __restrict__ gout
 #pragma unroll
     for (int k = 0; k < 12; ++k) {
       const float v = warp_sum(part[threadIdx.x][k]);
-      if (threadIdx.x == 0) gG[b * 12 + k] = v;
+      if (threadIdx.x == 0) partial[((int64_t)b * S + slice) * 12 + k] = v;
     }
   }
+}
+
+__global__ void drr_jac_bwd_finish_kernel(const float* __restrict__ partial, int B, int S, float* __restrict__ gG) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // one thread per (pose, matrix entry)
+  if (i >= B * 12) return;
+  const int b = i / 12, k = i - b * 12;
+  float v = 0.f;
+  for (int s = 0; s < S; ++s) v += partial[((int64_t)b * S + s) * 12 + k];
+  gG[i] = v;
 }
 
 static int g_ksplit = -1;  // -1: automatic
@@ -621,8 +634,19 @@ extern "C" int xvr_trilinear_drr_fwd(const float* volume, const void* voltex, in
 }
 
 // Backward of any fused DRR forward that saved its per-ray Jacobian: gG (B,3,4) = dL/d(cam2vox).
+// workspace: NULL (one CTA per pose) or >= 12 * B * xvr_drr_jac_bwd_slices(B, det_h * det_w) floats: small batches
+// (registration, B = 1) then spread each pose over several CTAs.
+extern "C" int xvr_drr_jac_bwd_slices(int B, int N) {
+  if (B <= 0 || N <= 0) return 1;
+  int S = (2 * 148 + B - 1) / B;             // about two CTAs per SM in total
+  const int most = (N + 2047) / 2048;         // at least two rays per thread and slice
+  if (S > most) S = most;
+  if (S > 64) S = 64;
+  return S < 1 ? 1 : S;
+}
+
 extern "C" int xvr_drr_jac_bwd(const float* jac, const float* gout, const float* det9, int B, int det_h, int det_w,
-                               float* gG, void* stream) {
+                               float* gG, float* workspace, void* stream) {
   if (!jac || !gout || !gG || B <= 0 || det_h <= 0) {
     set_last_error("xvr_drr_jac_bwd: invalid argument");
     return XVR_ERR_INVALID;
@@ -630,8 +654,18 @@ extern "C" int xvr_drr_jac_bwd(const float* jac, const float* gout, const float*
   DetectorGeom g = {};
   int rc = fill_geom(g, jac, jac, det9, det_w);  // the matrices are not read by the reduction
   if (rc) return rc;
-  drr_jac_bwd_kernel<<<B, 1024, 0, (cudaStream_t)stream>>>(jac, gout, det_h * det_w, g, gG);
-  return check_launch("xvr_drr_jac_bwd");
+  const int N = det_h * det_w;
+  const int S = workspace ? xvr_drr_jac_bwd_slices(B, N) : 1;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (S == 1) {
+    drr_jac_bwd_kernel<<<dim3(B, 1), 1024, 0, st>>>(jac, gout, N, g, gG);
+    return check_launch("xvr_drr_jac_bwd");
+  }
+  drr_jac_bwd_kernel<<<dim3(B, S), 1024, 0, st>>>(jac, gout, N, g, workspace);
+  rc = check_launch("xvr_drr_jac_bwd");
+  if (rc) return rc;
+  drr_jac_bwd_finish_kernel<<<(B * 12 + 127) / 128, 128, 0, st>>>(workspace, B, S, gG);
+  return check_launch("xvr_drr_jac_bwd/finish");
 }
 
 // Number of lanes that share one ray in the trilinear forward kernels, as log2 (0..3); -1 = automatic (grow until

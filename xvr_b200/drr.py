@@ -9,6 +9,7 @@ calls ``drr.detector(pose, None)``, ``drr.affine_inverse(points)``, ``drr.render
 ``perspective_projection`` / ``inverse_projection`` (/root/reference/src/xvr/metrics/evaluator.py:17-29).
 """
 
+import ctypes
 import os
 
 import numpy as np
@@ -18,7 +19,41 @@ from . import _conventions as conv
 from .pose import RigidTransform, convert
 from .renderers import Siddon, Trilinear
 
+from ._lib import call, cuda_f32, ptr, stream
+
 __all__ = ["DRR", "Detector"]
+
+
+class _EulerCamera(torch.autograd.Function):
+    """(rot, xyz) Euler pose -> (cam2vox, cam2world) (B,3,4) in ONE launch each way: the arithmetic of
+    ``convert(rot, xyz, "euler_angles", convention)`` -> ``reorient.compose(pose)`` -> ``affine_inverse @ ...``
+    (some 25 small launches, and twice as many in its autograd backward) as csrc/regstep.cu.  Used by
+    ``DRR.forward(rot, xyz, parameterization="euler_angles", ...)``, i.e. by ``Registration.forward``: at B = 1 the
+    launches around the renderer cost more than the renderer."""
+
+    @staticmethod
+    def forward(ctx, rot, xyz, axes, reorient16, affinv16):
+        rot, xyz = cuda_f32(rot, "rotation"), cuda_f32(xyz, "translation")
+        B = rot.shape[0]
+        if rot.shape != (B, 3) or xyz.shape != (B, 3):
+            raise ValueError(f"expected (B,3) Euler angles and (B,3) translations; got {tuple(rot.shape)}, {tuple(xyz.shape)}")
+        cam2world = torch.empty(B, 3, 4, device=rot.device, dtype=torch.float32)
+        cam2vox = torch.empty(B, 3, 4, device=rot.device, dtype=torch.float32)
+        ctx.consts = ((ctypes.c_int * 3)(*axes), int(conv.CONVERT_TRANSLATION_IN_ROTATED_FRAME),
+                      (ctypes.c_float * 16)(*reorient16), (ctypes.c_float * 16)(*affinv16))
+        call("xvr_euler_camera_fwd", ptr(rot), ptr(xyz), B, *ctx.consts, ptr(cam2world), ptr(cam2vox), stream())
+        ctx.save_for_backward(rot, xyz)
+        ctx.mark_non_differentiable(cam2world)  # only feeds the ray length, which a rigid motion leaves unchanged
+        return cam2vox, cam2world
+
+    @staticmethod
+    def backward(ctx, g_cam2vox, _g_cam2world):
+        rot, xyz = ctx.saved_tensors
+        B = rot.shape[0]
+        grot, gxyz = torch.empty_like(rot), torch.empty_like(xyz)
+        call("xvr_euler_camera_bwd", ptr(rot), ptr(xyz), B, *ctx.consts, ptr(cuda_f32(g_cam2vox, "grad")), ptr(grot),
+             ptr(gxyz), stream())
+        return grot, gxyz, None, None, None
 
 
 class Detector(torch.nn.Module):
@@ -154,16 +189,28 @@ class DRR(torch.nn.Module):
     def forward(self, *args, parameterization=None, convention=None, calibration=None, mask_to_channels=False,
                 **kwargs):
         """Render at ``pose`` (a RigidTransform) or at ``(rot, xyz, parameterization=, convention=)``."""
-        if parameterization is None:
-            (pose,) = args
-        else:
-            pose = convert(*args, parameterization=parameterization, convention=convention)
         if self.density is None:
             raise RuntimeError("drr.density was unloaded; call drr.renderer(volume, ...) directly "
                                "(as xvr's Trainer.render_samples does) or restore it")
         mask = getattr(self, "mask", None) if mask_to_channels else None
-        if (mask is None and calibration is None and isinstance(self.renderer, Trilinear) and self.reshape
-                and os.environ.get("XVR_B200_FUSED", "1") == "1"):
+        fused = (mask is None and calibration is None and isinstance(self.renderer, Trilinear) and self.reshape
+                 and os.environ.get("XVR_B200_FUSED", "1") == "1")
+        degrees = kwargs.pop("degrees", False)
+        if (fused and parameterization == "euler_angles" and len(args) == 2 and args[0].is_cuda and args[0].dim() == 2
+                and conv.COMPOSE_APPLIES_SELF_FIRST and os.environ.get("XVR_B200_FUSED_POSE", "1") == "1"):
+            # Euler parameters straight to camera matrices (one launch), then the fused renderer
+            rot, xyz = args
+            axes = ["XYZ".index(c) for c in convention]
+            reorient16, affinv16 = self._host_matrices()
+            cam2vox, cam2world = _EulerCamera.apply(torch.deg2rad(rot) if degrees else rot, xyz, axes, reorient16,
+                                                    affinv16)
+            img = self.renderer.render_drr(self.density, cam2vox, cam2world, self.detector, **kwargs)
+            return self.reshape_transform(img, batch_size=rot.shape[0])
+        if parameterization is None:
+            (pose,) = args
+        else:
+            pose = convert(*args, parameterization=parameterization, convention=convention, degrees=degrees)
+        if fused:
             # fused path: one kernel generates the rays, marches them and (if needed) emits the pose Jacobian
             cam2world = self.detector.reorient.compose(pose).matrix
             cam2vox = self._affine_inverse @ cam2world
@@ -176,6 +223,19 @@ class DRR(torch.nn.Module):
         target = self.affine_inverse(target)
         img = self.renderer(self.density, source, target, raylen, mask=mask, **kwargs)
         return self.reshape_transform(img, batch_size=len(pose))
+
+    def _host_matrices(self):
+        """Host copies (tuples of 16 floats) of the reorientation and the affine inverse for the one-launch pose
+        kernels; refreshed when either buffer is replaced or modified.  The device->host read happens on the first
+        call (before any CUDA-graph capture: captures are preceded by a warm-up run)."""
+        r, a = self.detector._reorient, self._affine_inverse
+        key = (r.data_ptr(), r._version, a.data_ptr(), a._version)
+        cache = getattr(self, "_host_matrix_cache", None)
+        if cache is None or cache[0] != key:
+            cache = (key, tuple(r.detach().double().cpu().flatten().tolist()),
+                     tuple(a.detach().double().cpu().flatten().tolist()))
+            self._host_matrix_cache = cache
+        return cache[1], cache[2]
 
     # ------------------------------------------------------------------ intrinsics
     def set_intrinsics_(self, sdd=None, delx=None, dely=None, x0=None, y0=None, height=None, width=None):

@@ -12,10 +12,12 @@ conversion, fused DRR forward (+ Jacobian), transforms, similarity forward/backw
 graph and replays it; the only per-iteration host round trip left is the scalar the plateau scheduler needs.
 """
 
+import ctypes
 import time
 
 import torch
 
+from ._lib import call, ptr, stream
 from .metrics import GradientNormalizedCrossCorrelation2d, MultiscaleNormalizedCrossCorrelation2d
 from .pose import convert
 from .preprocess import XrayTransforms
@@ -40,17 +42,24 @@ class PlateauScheduler:
     ``step(metric)`` must be called after the optimiser update of the iteration, as the reference does.
     """
 
-    def __init__(self, lrs, factor=0.1, patience=10, threshold=1e-4, min_lr=0.0, eps=1e-8, max_n_plateaus=3):
+    def __init__(self, lrs, factor=0.1, patience=10, threshold=1e-4, min_lr=0.0, eps=1e-8, max_n_plateaus=3,
+                 storage=None):
         dev = lrs[0].device
         self.lrs = lrs
         self.factor, self.patience, self.threshold, self.min_lr, self.eps = factor, patience, threshold, min_lr, eps
         self.max_n_plateaus = max_n_plateaus
         f64 = dict(device=dev, dtype=torch.float64)  # the reference's scheduler works in Python doubles
-        self.best = torch.full((), float("-inf"), **f64)
-        self.num_bad = torch.zeros((), **f64)
-        self.current_lr = torch.full((), float("inf"), **f64)
-        self.n_plateaus = torch.zeros((), **f64)
-        self.active = torch.ones((), **f64)  # 1 while the stage is running, 0 after the stopping rule fired
+        if storage is None:
+            storage = torch.zeros(5, **f64)
+        # `storage` (5 doubles: best, num_bad, smallest lr seen, n_plateaus, active) lets the fused update kernel
+        # (csrc/regstep.cu, xvr_reg_update) own the same state this class steps with tensor ops
+        self.best, self.num_bad, self.current_lr, self.n_plateaus, self.active = (storage[i] for i in range(5))
+        with torch.no_grad():
+            self.best.fill_(float("-inf"))
+            self.num_bad.zero_()
+            self.current_lr.fill_(float("inf"))
+            self.n_plateaus.zero_()
+            self.active.fill_(1.0)  # 1 while the stage is running, 0 after the stopping rule fired
 
     def state(self):
         return [self.best, self.num_bad, self.current_lr, self.n_plateaus, self.active, *self.lrs]
@@ -109,7 +118,7 @@ class Registrar:
 
     def __init__(self, drr, scales="8", n_itrs="500", parameterization="euler_angles", convention="ZXY", lr_rot=1e-2,
                  lr_xyz=1e0, patience=10, threshold=1e-4, max_n_plateaus=3, crop=0, equalize=False, mncc_patch_size=9,
-                 gncc_patch_size=11, sigma=0.0, beta=0.5, use_cuda_graph=True, poll_every=16):
+                 gncc_patch_size=11, sigma=0.0, beta=0.5, use_cuda_graph=True, poll_every=16, fused_update=True):
         self.drr = drr
         self.scales = scales.split(",") if isinstance(scales, str) else [str(s) for s in scales]
         self.n_itrs = [int(n) for n in n_itrs.split(",")] if isinstance(n_itrs, str) else [int(n) for n in n_itrs]
@@ -124,6 +133,8 @@ class Registrar:
         self.sim2 = GradientNormalizedCrossCorrelation2d(gncc_patch_size, sigma)
         self.use_cuda_graph = use_cuda_graph
         self.poll_every = max(1, int(poll_every))
+        # one launch for Adam + plateau scheduler + stopping rule + trajectory row instead of ~10^2 tensor ops
+        self.fused_update = fused_update
 
     def imagesim(self, x, y):
         return self.beta * self.sim1(x, y) + (1 - self.beta) * self.sim2(x, y)
@@ -136,6 +147,14 @@ class Registrar:
         pred = transform(reg())
         loss = self.imagesim(img, pred).sum()
         loss.backward()
+        if self.fused_update:
+            hyper = (ctypes.c_double * 9)(0.9, 0.999, 1e-8, sched.factor, sched.patience, sched.threshold, sched.min_lr,
+                                          sched.eps, sched.max_n_plateaus)
+            call("xvr_reg_update", ptr(reg.rotation), ptr(reg.translation), ptr(reg.rotation.grad.contiguous()),
+                 ptr(reg.translation.grad.contiguous()), reg.rotation.numel(), ptr(state["exp_avg"][0]),
+                 ptr(state["exp_avg_sq"][0]), ptr(state["exp_avg"][1]), ptr(state["exp_avg_sq"][1]), ptr(state["packed"]),
+                 ptr(loss.detach()), ptr(log["rows"]), ptr(log["count"]), log["rows"].shape[0], hyper, stream())
+            return
         with torch.no_grad():
             adam_maximize_([reg.rotation, reg.translation], [reg.rotation.grad, reg.translation.grad], state,
                            sched.lrs, active=sched.active)
@@ -169,11 +188,14 @@ class Registrar:
             img = transform(gt.to(device))
 
             step_size_scalar *= 2 ** (stage - 1)
-            lrs = [torch.tensor(self.lr_rot / step_size_scalar, device=device, dtype=torch.float64),
-                   torch.tensor(self.lr_xyz / step_size_scalar, device=device, dtype=torch.float64)]
+            # {Adam step, best, num_bad, smallest lr seen, n_plateaus, active, lr_rot, lr_xyz}: one buffer, viewed by
+            # the tensor-op implementations below and owned by xvr_reg_update when fused_update is on
+            packed = torch.zeros(8, device=device, dtype=torch.float64)
+            packed[6], packed[7] = self.lr_rot / step_size_scalar, self.lr_xyz / step_size_scalar
+            lrs = [packed[6], packed[7]]
             sched = PlateauScheduler(lrs, factor=0.1, patience=self.patience, threshold=self.threshold,
-                                     max_n_plateaus=self.max_n_plateaus)
-            state = {"step": torch.zeros((), device=device, dtype=torch.float64),
+                                     max_n_plateaus=self.max_n_plateaus, storage=packed[1:6])
+            state = {"step": packed[0], "packed": packed,
                      "exp_avg": [torch.zeros_like(reg.rotation), torch.zeros_like(reg.translation)],
                      "exp_avg_sq": [torch.zeros_like(reg.rotation), torch.zeros_like(reg.translation)]}
             log = {"rows": torch.zeros(max(n_itr, 1), 1 + n_rot + 3 + 2, device=device),

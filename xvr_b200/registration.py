@@ -27,4 +27,7 @@ class Registration(torch.nn.Module):
                        convention=self.convention)
 
     def forward(self, **kwargs):
-        return self.drr(self.pose, **kwargs)
+        # same image as drr(self.pose); handing over the parameters lets DRR.forward take its one-launch
+        # Euler -> camera path (csrc/regstep.cu) instead of the convert/compose chain
+        return self.drr(self.rotation, self.translation, parameterization=self.parameterization,
+                        convention=self.convention, **kwargs)

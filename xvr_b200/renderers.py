@@ -197,7 +197,9 @@ class _RenderDRR(torch.autograd.Function):
         gG = gvol = None
         if ctx.needs_input_grad[1]:
             gG = torch.empty(B, 3, 4, device=gout.device, dtype=torch.float32)
-            call("xvr_drr_jac_bwd", ptr(jac), ptr(gout), det, B, H, W, ptr(gG), stream())
+            slices = _lib.lib().xvr_drr_jac_bwd_slices(B, H * W)
+            work = torch.empty(12 * B * slices, device=gout.device, dtype=torch.float32) if slices > 1 else None
+            call("xvr_drr_jac_bwd", ptr(jac), ptr(gout), det, B, H, W, ptr(gG), ptr(work), stream())
         if ctx.needs_input_grad[0]:
             cam2vox, cam2world = mats
             full = torch.zeros(B, 4, 4, device=gout.device, dtype=torch.float64)
