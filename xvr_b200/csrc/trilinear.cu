@@ -480,14 +480,26 @@ static int fill_common(TrilinearParams& p, const float* volume, const void* volt
   p.n_points = n_points;
   p.step_mode = step_mode;
   p.eps = eps;
-  // small batches: let several lanes share a ray so that the machine has >= ~2 waves of threads
+  // Small batches (B = 1 registration): let 2, 4 or 8 lanes share a ray.  The kernel keeps 3 CTAs per SM resident,
+  // i.e. a "wave" is 444 CTAs; pick the split whose last wave is fullest (ceil(waves) / waves smallest), preferring
+  // fewer lanes per ray on ties.  Launches of more than ~16 waves are left alone: their tail is < 6 %.
   int ks = 0;
   if (!labels && allow_ksplit) {
     if (g_ksplit >= 0) {
       ks = g_ksplit;
     } else {
-      const int64_t want = 2LL * 148 * 3 * 256;
-      while (ks < 3 && (((int64_t)B * N) << ks) < want) ++ks;
+      const double wave = 148.0 * XVR_TRI_MIN_CTAS;
+      double best = 1e30;
+      for (int k = 0; k <= 3; ++k) {
+        const double ctas = (double)(((int64_t)B * N << k) + 255) / 256.0;
+        const double waves = ctas / wave;
+        if (k == 0 && waves >= 16.0) break;
+        const double cost = (waves < 1.0 ? 1.0 : ceil(waves)) / waves;
+        if (cost < best - 1e-9) {
+          best = cost;
+          ks = k;
+        }
+      }
     }
   }
   return fill_map(p.map, N, det_h, det_w, lane_w_log2, cta_w_log2, ks, &p.tiles_per_pose);
