@@ -21,6 +21,7 @@ ap.add_argument("--batch", type=int, default=116)
 ap.add_argument("--labels", action="store_true")
 ap.add_argument("--graph", action="store_true", help="replay the iteration as CUDA graphs (TrainStep(use_cuda_graph=True))")
 ap.add_argument("--log-every", type=int, default=4)
+ap.add_argument("--channels-last", action="store_true")
 args = ap.parse_args()
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
@@ -42,7 +43,8 @@ for seed in range(args.n_vols):
     volumes.append((hu, lab.float() if lab is not None else None, RigidTransform(torch.linalg.inv(aff)), offset))
 
 torch.manual_seed(0)
-model = PoseRegressor("resnet18", "quaternion_adjugate", "ZXY", height=args.height, norm_layer="groupnorm").to(dev)
+model = PoseRegressor("resnet18", "quaternion_adjugate", "ZXY", height=args.height, norm_layer="groupnorm",
+                      channels_last=args.channels_last).to(dev)
 step = TrainStep(drr, model, volumes, bench.POSE_RANGES, XrayTransforms(args.height), bench.SDD, batch_size=args.batch,
                  n_grad_accum_itrs=4, n_warmup_itrs=8, use_cuda_graph=args.graph,
                  log_every=args.log_every if args.graph else 1)
@@ -65,7 +67,7 @@ if world > 1:
 dt = time.time() - t0
 if rank == 0:
     print(json.dumps({"workload": f"xvr train step: {args.n_vols} x {args.vol}^3 volumes, batch {args.batch} sharded over {world} GPU(s), "
-                      f"{args.height}^2 DRRs, resnet18+GroupNorm, 2 renders/step, labels={args.labels}, cuda_graph={args.graph}",
+                      f"{args.height}^2 DRRs, resnet18+GroupNorm, 2 renders/step, labels={args.labels}, cuda_graph={args.graph}, channels_last={args.channels_last}",
                       "n_gpus": world, "ms_per_step": 1e3 * dt / args.steps, "steps_per_s": args.steps / dt,
                       "drrs_per_s": 2 * args.batch * args.steps / dt, "last_log": log}))
 if world > 1:

@@ -99,18 +99,51 @@ def test_one_launch_euler_camera_matches_the_tensor_chain(cuda, convention, monk
 
 def test_fused_update_matches_tensor_op_update(cuda):
     """xvr_reg_update (Adam + plateau scheduler + stopping rule + log row in one launch) against the tensor-op
-    implementations that tests/test_cpu_registrar.py pins to torch.optim: same trajectory, same stop iteration."""
-    res = []
-    for fused in (True, False):
-        drr, gt, init, *_ = _problem(cuda)
-        pose, info = Registrar(drr, scales="1", n_itrs="120", patience=3, max_n_plateaus=2, use_cuda_graph=True,
-                               fused_update=fused).run(gt, init)
-        res.append((pose.matrix.clone(), info))
-    a, b = res[0][1], res[1][1]
-    assert a["n_itrs"] == b["n_itrs"] and a["n_itrs"][0] < 120  # the stopping rule fired, at the same iteration
-    # same arithmetic, different association (fp32 products folded differently): the two optimisations drift apart
-    # by ~1e-4 in similarity over tens of iterations, far below anything the plateau logic reacts to
-    assert torch.allclose(torch.tensor(a["nccs"]), torch.tensor(b["nccs"]), atol=1e-3)
-    assert torch.allclose(torch.tensor(a["alphas"]), torch.tensor(b["alphas"]), rtol=1e-6, atol=0)
-    assert torch.allclose(torch.tensor(a["params"]), torch.tensor(b["params"]), rtol=2e-3, atol=2e-2)
-    assert torch.allclose(res[0][0], res[1][0], atol=2e-2)
+    implementations that tests/test_cpu_registrar.py pins to torch.optim, step by step on the SAME scripted
+    gradients and similarities (plateaus, a recovery, then the stop): parameters, moments, scheduler state and the
+    trajectory log must agree after every update."""
+    import ctypes
+
+    from xvr_b200._lib import call, ptr, stream
+    from xvr_b200.registrar import PlateauScheduler, adam_maximize_
+
+    g = torch.Generator().manual_seed(5)
+    n_steps, patience, max_plateaus = 40, 2, 4
+    losses = torch.cat([torch.linspace(0.5, 0.8, 8), torch.full((9,), 0.8), torch.tensor([0.9]), torch.full((22,), 0.9)])
+    grads = [(torch.randn(1, 3, generator=g).to(cuda), torch.randn(1, 3, generator=g).to(cuda) * 5) for _ in range(n_steps)]
+
+    def fresh():
+        packed = torch.zeros(8, device=cuda, dtype=torch.float64)
+        packed[6], packed[7] = 1e-2, 1.0
+        sched = PlateauScheduler([packed[6], packed[7]], patience=patience, max_n_plateaus=max_plateaus, storage=packed[1:6])
+        rot = torch.tensor([[0.1, -0.2, 0.3]], device=cuda)
+        xyz = torch.tensor([[5.0, 800.0, -10.0]], device=cuda)
+        m = [torch.zeros_like(rot), torch.zeros_like(xyz)]
+        v = [torch.zeros_like(rot), torch.zeros_like(xyz)]
+        rows = torch.zeros(n_steps, 9, device=cuda)
+        count = torch.zeros((), device=cuda)
+        return packed, sched, rot, xyz, m, v, rows, count
+
+    A = fresh()
+    B = fresh()
+    hyper = (ctypes.c_double * 9)(0.9, 0.999, 1e-8, 0.1, patience, 1e-4, 0.0, 1e-8, max_plateaus)
+    for i in range(n_steps):
+        loss = losses[i].to(cuda)
+        # fused
+        packed, sched, rot, xyz, m, v, rows, count = A
+        call("xvr_reg_update", ptr(rot), ptr(xyz), ptr(grads[i][0]), ptr(grads[i][1]), 3, ptr(m[0]), ptr(v[0]), ptr(m[1]),
+             ptr(v[1]), ptr(packed), ptr(loss), ptr(rows), ptr(count), n_steps, hyper, stream())
+        # tensor ops, in the order of Registrar._iteration
+        packed, sched, rot, xyz, m, v, rows, count = B
+        state = {"step": packed[0], "exp_avg": m, "exp_avg_sq": v}
+        adam_maximize_([rot, xyz], list(grads[i]), state, sched.lrs, active=sched.active)
+        was_active = sched.active.clone()
+        sched.step(loss)
+        if was_active.item() > 0:
+            rows[int(count.item())] = torch.cat([loss.reshape(1), rot.reshape(-1), xyz.reshape(-1), torch.stack(sched.lrs).float()])
+            count += 1
+        for name, x, y in (("state", A[0], B[0]), ("rot", A[2], B[2]), ("xyz", A[3], B[3]), ("m_rot", A[4][0], B[4][0]),
+                           ("v_xyz", A[5][1], B[5][1]), ("rows", A[6], B[6]), ("count", A[7], B[7])):
+            assert torch.allclose(x.double(), y.double(), rtol=2e-6, atol=1e-9), (i, name, x, y)
+    assert A[0][5].item() == 0.0 and A[7].item() < n_steps  # the stopping rule fired and froze the state
+    assert A[0][4].item() == max_plateaus

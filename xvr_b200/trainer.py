@@ -36,7 +36,7 @@ class PoseRegressor(torch.nn.Module):
     """CNN backbone (1 input channel, global-average-pooled features) + two linear heads -> RigidTransform."""
 
     def __init__(self, model_name="resnet18", parameterization="quaternion_adjugate", convention="ZXY", pretrained=False,
-                 height=256, unit_conversion_factor=1000.0, norm_layer="groupnorm", **kwargs):
+                 height=256, unit_conversion_factor=1000.0, norm_layer="groupnorm", channels_last=False, **kwargs):
         super().__init__()
         import torchvision  # noqa: PLC0415 - the reference uses timm, which is not available offline
 
@@ -58,8 +58,14 @@ class PoseRegressor(torch.nn.Module):
         self.xyz_regression = torch.nn.Linear(features, 3)
         self.rot_regression = torch.nn.Linear(features, N_ANGULAR_COMPONENTS[parameterization])
         self.unit_conversion_factor = unit_conversion_factor
+        # NHWC activations: cuDNN's tensor-core convolutions stop converting NCHW <-> NHWC around every layer
+        self.channels_last = bool(channels_last)
+        if self.channels_last:
+            self.backbone.to(memory_format=torch.channels_last)
 
     def forward(self, x):
+        if self.channels_last:
+            x = x.contiguous(memory_format=torch.channels_last)
         x = self.backbone(x)
         rot = self.rot_regression(x)
         xyz = self.unit_conversion_factor * self.xyz_regression(x)
