@@ -32,10 +32,6 @@ long long xvr_launch_count(void);
 int xvr_volume_create(int D0, int D1, int D2, void** handle_out);
 int xvr_volume_upload(void* handle, const float* volume, void* stream);
 int xvr_volume_destroy(void* handle);
-/* the label map (uint8) in the same layout, for the multi-channel renderers: `labtex` below, or NULL to gather the
- * labels from the linear uint8 volume; destroyed with xvr_volume_destroy */
-int xvr_labels_create(int D0, int D1, int D2, void** handle_out);
-int xvr_labels_upload(void* handle, const unsigned char* labels, void* stream);
 
 /* ---- Trilinear renderer = diffdrr.renderers.Trilinear.forward
  * call site /root/reference/src/xvr/model/trainer.py:288  drr.renderer(vol, source, target, raylen, mask=seg)
@@ -44,14 +40,12 @@ int xvr_labels_upload(void* handle, const unsigned char* labels, void* stream);
  *   out (B,C,N);  jac (B,7,N) or NULL: per-ray d(sum over channels of out)/d(source xyz, target xyz, raylen) --
  *   with labels this serves callers that collapse the channels (trainer.py:294), others use xvr_*_rays_bwd */
 int xvr_trilinear_rays_fwd(const float* volume, const void* voltex, int D0, int D1, int D2, const uint8_t* labels,
-                           const void* labtex,
                            int C, const float* source, const float* target, const float* raylen, int B, int N,
                            int n_points, int step_mode, float eps, int det_h, int det_w, int lane_w_log2,
                            int cta_w_log2, float* out, float* jac, void* stream);
 /* autograd backward of the above (= grid_sample backward + glue): re-marches the rays.
  *   gout (B,C,N) -> gsource (B,1,3), gtarget (B,N,3), graylen (B,N); workspace (B,3,N) */
 int xvr_trilinear_rays_bwd(const float* volume, const void* voltex, int D0, int D1, int D2, const uint8_t* labels,
-                           const void* labtex,
                            int C, const float* source, const float* target, const float* raylen, int B, int N,
                            int n_points, int step_mode, float eps, int det_h, int det_w, int lane_w_log2,
                            int cta_w_log2, const float* gout, float* gsource, float* gtarget, float* graylen,

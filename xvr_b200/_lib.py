@@ -21,13 +21,11 @@ _SIGNATURES = {
     "xvr_volume_create": ([c_int, c_int, c_int, ctypes.POINTER(c_void_p)], c_int),
     "xvr_volume_upload": ([P, P, P], c_int),
     "xvr_volume_destroy": ([P], c_int),
-    "xvr_labels_create": ([c_int, c_int, c_int, ctypes.POINTER(c_void_p)], c_int),
-    "xvr_labels_upload": ([P, P, P], c_int),
     "xvr_trilinear_rays_fwd": (
-        [P, P, c_int, c_int, c_int, P, P, c_int, P, P, P, c_int, c_int, c_int, c_int, c_float, c_int, c_int, c_int,
+        [P, P, c_int, c_int, c_int, P, c_int, P, P, P, c_int, c_int, c_int, c_int, c_float, c_int, c_int, c_int,
          c_int, P, P, P], c_int),
     "xvr_trilinear_rays_bwd": (
-        [P, P, c_int, c_int, c_int, P, P, c_int, P, P, P, c_int, c_int, c_int, c_int, c_float, c_int, c_int, c_int,
+        [P, P, c_int, c_int, c_int, P, c_int, P, P, P, c_int, c_int, c_int, c_int, c_float, c_int, c_int, c_int,
          c_int, P, P, P, P, P, P], c_int),
     "xvr_trilinear_drr_fwd": (
         [P, P, c_int, c_int, c_int, P, P, ctypes.POINTER(c_float), c_int, c_int, c_int, c_int, c_int, c_float, c_int,

@@ -37,28 +37,25 @@ extern "C" long long xvr_launch_count(void) { return xvr::g_launches; }
 // A second, block-linear copy of the CT volume (cudaArray, layered 2D: layer = axis 0 + 1, with one zero layer at
 // each end) behind a point-sampled texture object.  The trilinear kernels fetch the 2x2 (axis 1, axis 2) corner footprint of each of the two
 // layers with one TLD4 each instead of 8 scalar loads.
-// Layered array with D0 + 2 layers (0 and D0 + 1 zeroed here, never written again) + point-sampled border texture.
-static int create_layered(const char* what, int D0, int D1, int D2, cudaChannelFormatDesc desc, size_t elem,
-                          void** out) {
+extern "C" int xvr_volume_create(int D0, int D1, int D2, void** out) {
   if (!out || D0 < 1 || D1 < 1 || D2 < 1 || D0 > 2046 || D1 > 32768 || D2 > 32768) {
-    char msg[256];
-    snprintf(msg, sizeof(msg), "%s: invalid shape (layered 2D arrays hold <= 2048 layers of <= 32768^2, two of which "
-             "are the zero padding)", what);
-    xvr::set_last_error(msg);
+    xvr::set_last_error("xvr_volume_create: invalid shape (layered 2D arrays hold <= 2048 layers of <= 32768^2, "
+                        "two of which are the zero padding)");
     return XVR_ERR_INVALID;
   }
   xvr::VolumeTexture* vt = new xvr::VolumeTexture();
   vt->D0 = D0;
   vt->D1 = D1;
   vt->D2 = D2;
+  cudaChannelFormatDesc desc = cudaCreateChannelDesc<float>();
   cudaError_t e = cudaMalloc3DArray(&vt->array, &desc, make_cudaExtent(D2, D1, D0 + 2), cudaArrayLayered);
   if (e == cudaSuccess) {  // zero the two padding layers (0 and D0 + 1) once; uploads never touch them
-    void* zeros = nullptr;
-    e = cudaMalloc(&zeros, (size_t)D1 * D2 * elem);
-    if (e == cudaSuccess) e = cudaMemset(zeros, 0, (size_t)D1 * D2 * elem);
+    float* zeros = nullptr;
+    e = cudaMalloc(&zeros, (size_t)D1 * D2 * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemset(zeros, 0, (size_t)D1 * D2 * sizeof(float));
     for (int layer = 0; layer <= D0 + 1 && e == cudaSuccess; layer += D0 + 1) {
       cudaMemcpy3DParms cp = {};
-      cp.srcPtr = make_cudaPitchedPtr(zeros, (size_t)D2 * elem, D2, D1);
+      cp.srcPtr = make_cudaPitchedPtr(zeros, (size_t)D2 * sizeof(float), D2, D1);
       cp.dstArray = vt->array;
       cp.dstPos = make_cudaPos(0, 0, layer);
       cp.extent = make_cudaExtent(D2, D1, 1);
@@ -82,7 +79,7 @@ static int create_layered(const char* what, int D0, int D1, int D2, cudaChannelF
   }
   if (e != cudaSuccess) {
     char msg[256];
-    snprintf(msg, sizeof(msg), "%s: %s", what, cudaGetErrorString(e));
+    snprintf(msg, sizeof(msg), "xvr_volume_create: %s", cudaGetErrorString(e));
     xvr::set_last_error(msg);
     cudaGetLastError();
     delete vt;
@@ -92,16 +89,14 @@ static int create_layered(const char* what, int D0, int D1, int D2, cudaChannelF
   return XVR_OK;
 }
 
-static int upload_layered(const char* what, void* handle, const void* src, size_t elem, void* stream) {
+extern "C" int xvr_volume_upload(void* handle, const float* volume, void* stream) {
   xvr::VolumeTexture* vt = (xvr::VolumeTexture*)handle;
-  if (!vt || !src) {
-    char msg[128];
-    snprintf(msg, sizeof(msg), "%s: null argument", what);
-    xvr::set_last_error(msg);
+  if (!vt || !volume) {
+    xvr::set_last_error("xvr_volume_upload: null argument");
     return XVR_ERR_INVALID;
   }
   cudaMemcpy3DParms cp = {};
-  cp.srcPtr = make_cudaPitchedPtr((void*)src, (size_t)vt->D2 * elem, vt->D2, vt->D1);
+  cp.srcPtr = make_cudaPitchedPtr((void*)volume, (size_t)vt->D2 * sizeof(float), vt->D2, vt->D1);
   cp.dstArray = vt->array;
   cp.dstPos = make_cudaPos(0, 0, 1);  // array layer 0 is zero padding
   cp.extent = make_cudaExtent(vt->D2, vt->D1, vt->D0);
@@ -109,31 +104,12 @@ static int upload_layered(const char* what, void* handle, const void* src, size_
   cudaError_t e = cudaMemcpy3DAsync(&cp, (cudaStream_t)stream);
   if (e != cudaSuccess) {
     char msg[256];
-    snprintf(msg, sizeof(msg), "%s: %s", what, cudaGetErrorString(e));
+    snprintf(msg, sizeof(msg), "xvr_volume_upload: %s", cudaGetErrorString(e));
     xvr::set_last_error(msg);
     cudaGetLastError();
     return XVR_ERR_CUDA;
   }
   return XVR_OK;
-}
-
-extern "C" int xvr_volume_create(int D0, int D1, int D2, void** out) {
-  return create_layered("xvr_volume_create", D0, D1, D2, cudaCreateChannelDesc<float>(), sizeof(float), out);
-}
-
-extern "C" int xvr_volume_upload(void* handle, const float* volume, void* stream) {
-  return upload_layered("xvr_volume_upload", handle, volume, sizeof(float), stream);
-}
-
-// The label map (uint8) in the same layout: the nearest-label lookup of the multi-channel renderers becomes one
-// point fetch on the texture pipe instead of a scattered 1-byte load on the LSU path (which shares its data stage
-// with the corner gathers).  Destroyed with xvr_volume_destroy.
-extern "C" int xvr_labels_create(int D0, int D1, int D2, void** out) {
-  return create_layered("xvr_labels_create", D0, D1, D2, cudaCreateChannelDesc<unsigned char>(), 1, out);
-}
-
-extern "C" int xvr_labels_upload(void* handle, const unsigned char* labels, void* stream) {
-  return upload_layered("xvr_labels_upload", handle, labels, 1, stream);
 }
 
 extern "C" int xvr_volume_destroy(void* handle) {

@@ -194,14 +194,6 @@ __device__ __forceinline__ int sample_label(const uint8_t* __restrict__ lab, con
   return (int)__ldg(lab + ((int64_t)(int)rx * v.s0 + (int)ry * v.s1 + (int)rz));
 }
 
-// The same lookup on the label texture (xvr_labels_create: array layer = axis 0 + 1, zero layers at both ends,
-// border mode on axes 1/2): one point fetch on the texture pipe; out-of-range coordinates read label 0.
-__device__ __forceinline__ int sample_label_tex(cudaTextureObject_t tex, const Vol& v, float x, float y, float z) {
-  const float rx = nearbyintf(x), ry = nearbyintf(y), rz = nearbyintf(z);
-  const int layer = (int)min((unsigned)((int)rx + 1), (unsigned)(v.D0 + 1));
-  return (int)tex2DLayered<unsigned char>(tex, rz + 0.5f, ry + 0.5f, layer);
-}
-
 // Thread -> detector pixel mapping.  A CTA of 256 threads covers a (256>>cta_w_log2) x (1<<cta_w_log2) pixel
 // tile; inside it each warp covers a (32>>lane_w_log2) x (1<<lane_w_log2) sub-tile, so that the 32 lanes of a
 // gather touch as few 128-byte lines of the volume as the view geometry allows.

@@ -21,7 +21,6 @@ namespace xvr {
 struct TrilinearParams {
   Vol vol;
   const uint8_t* __restrict__ labels;  // nullable, same shape as vol
-  cudaTextureObject_t labtex;          // optional texture copy of `labels` (0: gather through the LSU path)
   int C;                               // output channels (1 without labels)
   const float* __restrict__ source;    // (B,1,3) voxel coords
   const float* __restrict__ target;    // (B,N,3)
@@ -118,7 +117,7 @@ __global__ void __launch_bounds__(256, XVR_TRI_MIN_CTAS) trilinear_fwd_kernel(co
       float g[3];
       const float v = sample_trilinear<JAC, TEX>(p.vol, x, y, z, g);
       if (LABELS) {
-        const int c = p.labtex ? sample_label_tex(p.labtex, p.vol, x, y, z) : sample_label(p.labels, p.vol, x, y, z);
+        const int c = sample_label(p.labels, p.vol, x, y, z);
         chan_acc[c * 256 + tid] += v;
       } else {
         sumV += v;
@@ -258,8 +257,7 @@ __global__ void __launch_bounds__(256) trilinear_bwd_kernel(const TrilinearParam
       float g[3];
       const float v = sample_trilinear<true, TEX>(p.vol, x, y, z, g);
       float go = g1;
-      if (LABELS)
-        go = chan_g[(p.labtex ? sample_label_tex(p.labtex, p.vol, x, y, z) : sample_label(p.labels, p.vol, x, y, z)) * 256 + tid];
+      if (LABELS) go = chan_g[sample_label(p.labels, p.vol, x, y, z) * 256 + tid];
       sumV = fmaf(go, v, sumV);
 #pragma unroll
       for (int a = 0; a < 3; ++a) {
@@ -444,7 +442,7 @@ static int fill_map(TileMap& m, int N, int det_h, int det_w, int lane_w_log2, in
 }
 
 static int fill_common(TrilinearParams& p, const float* volume, const void* voltex, int D0, int D1, int D2,
-                       const uint8_t* labels, const void* labtex,
+                       const uint8_t* labels,
                        int C, const float* source, const float* target, const float* raylen, int B, int N,
                        int n_points, int step_mode, float eps, int det_h, int det_w, int lane_w_log2,
                        int cta_w_log2, bool allow_ksplit = true) {
@@ -473,15 +471,6 @@ static int fill_common(TrilinearParams& p, const float* volume, const void* volt
     p.vol.tex = vt->tex;
   }
   p.labels = labels;
-  p.labtex = 0;
-  if (labels && labtex) {
-    const VolumeTexture* lt = (const VolumeTexture*)labtex;
-    if (lt->D0 != D0 || lt->D1 != D1 || lt->D2 != D2) {
-      set_last_error("xvr_trilinear: label texture shape differs from the volume");
-      return XVR_ERR_INVALID;
-    }
-    p.labtex = lt->tex;
-  }
   p.C = C;
   p.source = source;
   p.target = target;
@@ -521,13 +510,13 @@ static int fill_common(TrilinearParams& p, const float* volume, const void* volt
 using namespace xvr;
 
 extern "C" int xvr_trilinear_rays_fwd(const float* volume, const void* voltex, int D0, int D1, int D2,
-                                      const uint8_t* labels, const void* labtex, int C,
+                                      const uint8_t* labels, int C,
                                       const float* source, const float* target, const float* raylen, int B,
                                       int N, int n_points, int step_mode, float eps, int det_h, int det_w,
                                       int lane_w_log2, int cta_w_log2, float* out, float* jac, void* stream) {
   TrilinearParams p = {};
-  int rc = fill_common(p, volume, voltex, D0, D1, D2, labels, labtex, C, source, target, raylen, B, N, n_points,
-                       step_mode, eps, det_h, det_w, lane_w_log2, cta_w_log2);
+  int rc = fill_common(p, volume, voltex, D0, D1, D2, labels, C, source, target, raylen, B, N, n_points, step_mode, eps,
+                       det_h, det_w, lane_w_log2, cta_w_log2);
   if (rc) return rc;
   if (!out) {
     set_last_error("xvr_trilinear_rays_fwd: out is null");
@@ -560,14 +549,14 @@ extern "C" int xvr_trilinear_rays_fwd(const float* volume, const void* voltex, i
 }
 
 extern "C" int xvr_trilinear_rays_bwd(const float* volume, const void* voltex, int D0, int D1, int D2,
-                                      const uint8_t* labels, const void* labtex, int C,
+                                      const uint8_t* labels, int C,
                                       const float* source, const float* target, const float* raylen, int B,
                                       int N, int n_points, int step_mode, float eps, int det_h, int det_w,
                                       int lane_w_log2, int cta_w_log2, const float* gout, float* gsource,
                                       float* gtarget, float* graylen, float* workspace, void* stream) {
   TrilinearParams p = {};
-  int rc = fill_common(p, volume, voltex, D0, D1, D2, labels, labtex, C, source, target, raylen, B, N, n_points,
-                       step_mode, eps, det_h, det_w, lane_w_log2, cta_w_log2, false);
+  int rc = fill_common(p, volume, voltex, D0, D1, D2, labels, C, source, target, raylen, B, N, n_points, step_mode, eps,
+                       det_h, det_w, lane_w_log2, cta_w_log2, false);
   if (rc) return rc;
   if (!gout || !gsource || !gtarget || !graylen || !workspace) {
     set_last_error("xvr_trilinear_rays_bwd: null gradient buffer");
@@ -630,8 +619,8 @@ extern "C" int xvr_trilinear_drr_fwd(const float* volume, const void* voltex, in
   p.fused = true;
   int rc = fill_geom(p.geom, cam2vox, cam2world, det9, det_w);
   if (rc) return rc;
-  rc = fill_common(p, volume, voltex, D0, D1, D2, nullptr, nullptr, 1, nullptr, nullptr, nullptr, B, det_h * det_w,
-                   n_points, step_mode, eps, det_h, det_w, lane_w_log2, cta_w_log2);
+  rc = fill_common(p, volume, voltex, D0, D1, D2, nullptr, 1, nullptr, nullptr, nullptr, B, det_h * det_w, n_points,
+                   step_mode, eps, det_h, det_w, lane_w_log2, cta_w_log2);
   if (rc) return rc;
   if (!out) {
     set_last_error("xvr_trilinear_drr_fwd: out is null");

@@ -78,51 +78,27 @@ class _VolumeTexture:
 
 
 class _LabelCache:
-    """uint8 copies of label volumes (+ their channel counts and, for the trilinear renderer, texture copies), one
-    entry per source tensor and version.  Several entries stay alive at once: a training run alternates between
-    subjects, and CUDA graphs captured for one subject keep raw pointers into its entry."""
+    """uint8 copy of a label volume and its channel count, refreshed when the source tensor changes."""
 
-    MAX_ENTRIES = 32
-
-    def __init__(self, with_texture=False):
-        self.with_texture = with_texture
-        self.entries = {}  # key -> (labels uint8, channels, texture handle or None); insertion order = age
+    def __init__(self):
+        self.key = None
+        self.labels = None
+        self.channels = 1
 
     def __deepcopy__(self, memo):
-        return _LabelCache(self.with_texture)
+        return _LabelCache()
 
     def get(self, mask):
         key = (mask.data_ptr(), mask._version, tuple(mask.shape), mask.dtype, mask.device)
-        hit = self.entries.get(key)
-        if hit is None:
+        if key != self.key:
             hi = int(mask.max().item())  # same host sync as the reference's `int(mask.max()) + 1`
             lo = int(mask.min().item())
             if lo < 0 or hi > 254:
                 raise _lib.XvrB200Error(f"label volume must hold integers in [0, 254]; got [{lo}, {hi}]")
-            labels = mask.to(torch.uint8).contiguous()
-            handle = None
-            if self.with_texture and os.environ.get("XVR_B200_GATHER", "tex") != "ldg" and labels.dim() == 3:
-                handle = ctypes.c_void_p()
-                with torch.cuda.device(labels.device):
-                    call("xvr_labels_create", *labels.shape, ctypes.byref(handle))
-                call("xvr_labels_upload", handle, ptr(labels), stream())
-            while len(self.entries) >= self.MAX_ENTRIES:
-                self._drop(next(iter(self.entries)))
-            hit = (labels, hi + 1, handle)
-            self.entries[key] = hit
-        return hit
-
-    def _drop(self, key):
-        _, _, handle = self.entries.pop(key)
-        if handle is not None:
-            try:
-                _lib.lib().xvr_volume_destroy(handle)
-            except Exception:  # noqa: BLE001 - interpreter shutdown
-                pass
-
-    def __del__(self):
-        for key in list(self.entries):
-            self._drop(key)
+            self.labels = mask.to(torch.uint8).contiguous()
+            self.channels = hi + 1
+            self.key = key
+        return self.labels, self.channels
 
 
 def _check_rays(volume, source, target, raylen):
@@ -148,7 +124,7 @@ class _RenderRays(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, volume, source, target, raylen, labels, C, kind, args, det_hw, voltex, labtex=None):
+    def forward(ctx, volume, source, target, raylen, labels, C, kind, args, det_hw, voltex):
         source, target, raylen = cuda_f32(source, "source"), cuda_f32(target, "target"), cuda_f32(raylen, "raylen")
         B, N = _check_rays(volume, source, target, raylen)
         if ctx.needs_input_grad[0]:
@@ -161,8 +137,7 @@ class _RenderRays(torch.autograd.Function):
         # channels (trainer.py:294 img.sum(dim=1)); backward() falls back to the recompute kernel otherwise
         jac = torch.empty(B, 7, N, device=volume.device, dtype=torch.float32) if need_pose_grad else None
         vol_args = (ptr(volume),) if voltex is False else (ptr(volume), voltex)
-        lab_args = (ptr(labels),) if voltex is False else (ptr(labels), labtex)  # Siddon takes no textures
-        ctx.common = (*vol_args, *volume.shape, *lab_args, C, ptr(source), ptr(target), ptr(raylen), B, N, *args,
+        ctx.common = (*vol_args, *volume.shape, ptr(labels), C, ptr(source), ptr(target), ptr(raylen), B, N, *args,
                       det_h, det_w, lw, cw)
         call(f"xvr_{kind}_rays_fwd", *ctx.common, ptr(out), ptr(jac), stream())
         ctx.kind = kind
@@ -191,7 +166,7 @@ class _RenderRays(torch.autograd.Function):
         else:
             call(f"xvr_{ctx.kind}_rays_bwd", *ctx.common, ptr(gout), ptr(gsource), ptr(gtarget), ptr(graylen),
                  ptr(work), stream())
-        return None, gsource, gtarget, graylen, None, None, None, None, None, None, None
+        return None, gsource, gtarget, graylen, None, None, None, None, None, None
 
 
 class _RenderDRR(torch.autograd.Function):
@@ -251,7 +226,7 @@ class Trilinear(torch.nn.Module):
         self.eps = eps
         self.step = step
         self.detector_hw = None  # set by DRR so that warps map to compact detector tiles
-        self._labels = _LabelCache(with_texture=True)
+        self._labels = _LabelCache()
         self._texture = _VolumeTexture()
 
     def dims(self, volume):
@@ -261,11 +236,11 @@ class Trilinear(torch.nn.Module):
                 mask=None):
         if not align_corners:
             raise NotImplementedError("xvr_b200.Trilinear implements align_corners=True (the DiffDRR default)")
-        labels, C, labtex = (None, 1, None) if mask is None else self._labels.get(mask)
+        labels, C = (None, 1) if mask is None else self._labels.get(mask)
         volume = cuda_f32(volume, "volume")
         return _RenderRays.apply(volume, source, target, img, labels, C, "trilinear",
                                  (int(n_points), conv.STEP_MODES[self.step], float(self.eps)), self.detector_hw,
-                                 self._texture.get(volume), labtex)
+                                 self._texture.get(volume))
 
 
     def render_drr(self, volume, cam2vox, cam2world, detector, n_points=conv.TRILINEAR_N_POINTS):
@@ -299,6 +274,6 @@ class Siddon(torch.nn.Module):
         return torch.tensor(volume.shape).to(volume) + 1
 
     def forward(self, volume, source, target, img, mask=None):
-        labels, C, _ = (None, 1, None) if mask is None else self._labels.get(mask)
+        labels, C = (None, 1) if mask is None else self._labels.get(mask)
         return _RenderRays.apply(cuda_f32(volume, "volume"), source, target, img, labels, C, "siddon",
                                  (float(self.voxel_shift), float(self.eps)), self.detector_hw, False)
