@@ -56,3 +56,25 @@ def test_warmup_cosine_schedule_matches_the_reference():
     g = GOLD["schedule"]
     assert torch.equal(_lrs(lambda o: WarmupCosineSchedule(o, 250, 2500), 300), g["warmup_cosine_250_of_2500"])
     assert torch.equal(_lrs(lambda o: WarmupCosineSchedule(o, 2.5, 40.0), 45), g["warmup_cosine_fractional"])
+
+
+def test_random_pose_draws_match_the_reference_sampler():
+    """model/sampler.py: six uniform draws of (n,1) in a fixed order from the global CPU generator, angles
+    circle-shifted to [-180, 180), handed to convert(..., 'euler_angles', 'ZXY', degrees=True)."""
+    from xvr_b200.sampler import random_pose_params
+
+    s = GOLD["sampler"]
+    torch.manual_seed(s["seed"])
+    rot, xyz = random_pose_params(**s["ranges"], batch_size=s["batch_size"])
+    assert torch.equal(rot, s["rot"]) and torch.equal(xyz, s["xyz"])
+    assert s["convert_kwargs"] == dict(parameterization="euler_angles", convention="ZXY", degrees=True)
+    assert rot[:, 1].min() >= -180 and rot[:, 1].max() < 180  # beta range [-170, 190) wraps
+
+
+def test_dice_loss_matches_the_reference():
+    from xvr_b200.trainer import DiceLoss
+
+    d = GOLD["dice"]
+    ours = DiceLoss()(d["a"], d["b"])
+    assert torch.allclose(ours, d["loss"], atol=1e-7, equal_nan=True)
+    assert ours[2].item() == 1.0  # no foreground anywhere: nanmean -> nan -> 0 -> loss 1
