@@ -147,3 +147,35 @@ def test_fused_update_matches_tensor_op_update(cuda):
             assert torch.allclose(x.double(), y.double(), rtol=2e-6, atol=1e-9), (i, name, x, y)
     assert A[0][5].item() == 0.0 and A[7].item() < n_steps  # the stopping rule fired and froze the state
     assert A[0][4].item() == max_plateaus
+
+
+def test_registrar_follows_the_genuine_reference_loop(cuda):
+    """tests/golden/reference_loop_v1.pt: xvr's own run_test_time_optimization (unmodified) on the oracle renderer.
+    Our graph-captured loop on the CUDA renderer must see the same similarities, drop the learning rates at the same
+    iterations, stop after the same iteration and end at the same pose."""
+    import os
+
+    from tests.golden.make_golden import scene
+    from xvr_b200.data import read
+
+    gold = torch.load(os.path.join(os.path.dirname(__file__), "golden", "reference_loop_v1.pt"), weights_only=False)
+    sc, h = gold["scene"], gold["hyper"]
+    hu, _, affine = scene(sc["n"])
+    drr = xvr_b200.DRR(read(hu, affine=affine, center_volume=False), sc["sdd"], sc["height"], sc["delx"],
+                       renderer="trilinear", reverse_x_axis=False).to(cuda)
+    rot0, xyz0 = gold["rot0"].to(cuda), gold["xyz0"].to(cuda)
+    with torch.no_grad():
+        gt = drr(xvr_b200.convert(rot0, xyz0, parameterization="euler_angles", convention="ZXY"))
+    assert rel_l2(gt.cpu(), gold["gt"]) < 1e-4
+    init = xvr_b200.convert(rot0 + gold["drot"].to(cuda), xyz0 + gold["dxyz"].to(cuda), parameterization="euler_angles",
+                            convention="ZXY")
+    reg = Registrar(drr, scales="1", n_itrs=str(h["n_itrs"][0]), lr_rot=h["lr_rot"], lr_xyz=h["lr_xyz"],
+                    patience=h["patience"], threshold=h["threshold"], max_n_plateaus=h["max_n_plateaus"])
+    _, info = reg.run(gt, init)
+    n = len(gold["nccs"]) - 1
+    assert info["n_itrs"] == [n]
+    assert (torch.tensor(info["nccs"], dtype=torch.float64) - gold["nccs"]).abs().max().item() < 2e-3
+    assert torch.allclose(torch.tensor(info["alphas"], dtype=torch.float64), gold["alphas"], rtol=1e-6)
+    ours = torch.tensor(info["params"], dtype=torch.float64)
+    assert (ours[:, :3] - gold["params"][:, :3]).abs().max().item() < 2e-3
+    assert (ours[:, 3:] - gold["params"][:, 3:]).abs().max().item() < 0.2
