@@ -115,7 +115,10 @@ def main():
         params, nccs, times, alphas = base._RegistrarBase.run_test_time_optimization(me, gt, reg, [1.0], imagesim)
     finally:
         torch.Tensor.cuda, torch.cuda.synchronize = patched
+    cases = [("8", 0, 256), ("8,4,2", 0, 256), ("1", 0, 256), ("8", 100, 1436), ("16,8,4,2", 64, 512)]
+    scales = {c: base._parse_scales(c[0].split(","), c[1], c[2]) for c in cases}  # base.py:77 splits the string first
     out = {"source": "src/xvr/registrar/base.py:198-292 (run_test_time_optimization), unmodified",
+           "parse_scales": scales,
            "scene": dict(n=N_VOL, height=HEIGHT, delx=DELX, sdd=SDD), "hyper": HYPER, "rot0": rot0, "xyz0": xyz0,
            "drot": torch.tensor(DROT), "dxyz": torch.tensor(DXYZ), "gt": gt,
            "params": torch.tensor(params, dtype=torch.float64), "nccs": torch.tensor(nccs, dtype=torch.float64),

@@ -26,3 +26,10 @@ def test_plateau_scheduler_replays_the_reference_run():
         assert abs(float(lrs[0]) - float(alphas[i + 1, 0])) < 1e-15
         assert abs(float(lrs[1]) - float(alphas[i + 1, 1])) < 1e-15
     assert sched.active == 0 and float(sched.n_plateaus) == h["max_n_plateaus"]
+
+
+def test_parse_scales_matches_the_reference():
+    from xvr_b200.registrar import parse_scales
+
+    for (scales, crop, height), ref in GOLD["parse_scales"].items():
+        assert parse_scales(scales, crop, height) == ref
