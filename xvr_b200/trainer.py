@@ -36,23 +36,29 @@ class PoseRegressor(torch.nn.Module):
     """CNN backbone (1 input channel, global-average-pooled features) + two linear heads -> RigidTransform."""
 
     def __init__(self, model_name="resnet18", parameterization="quaternion_adjugate", convention="ZXY", pretrained=False,
-                 height=256, unit_conversion_factor=1000.0, norm_layer="groupnorm", channels_last=False, **kwargs):
+                 height=256, unit_conversion_factor=1000.0, norm_layer="groupnorm", channels_last=False,
+                 backbone=None, **kwargs):
         super().__init__()
-        import torchvision  # noqa: PLC0415 - the reference uses timm, which is not available offline
-
-        if pretrained:
-            raise NotImplementedError("pretrained backbones need network access")
-        if norm_layer == "groupnorm":
-            norm = lambda c: torch.nn.GroupNorm(32, c)  # noqa: E731
-        elif norm_layer in ("batchnorm", "batchnorm2d", None):
-            norm = None
+        if backbone is not None:
+            # any feature extractor (B,1,H,W) -> (B,F); F probed like the reference does (network.py:40)
+            with torch.no_grad():
+                features = backbone(torch.randn(1, 1, height, height)).shape[-1]
         else:
-            raise ValueError(f"unknown norm_layer {norm_layer!r}")
-        backbone = getattr(torchvision.models, model_name)(norm_layer=norm, **kwargs)
-        old = backbone.conv1
-        backbone.conv1 = torch.nn.Conv2d(1, old.out_channels, old.kernel_size, old.stride, old.padding, bias=False)
-        features = backbone.fc.in_features
-        backbone.fc = torch.nn.Identity()
+            import torchvision  # noqa: PLC0415 - the reference uses timm, which is not available offline
+
+            if pretrained:
+                raise NotImplementedError("pretrained backbones need network access")
+            if norm_layer == "groupnorm":
+                norm = lambda c: torch.nn.GroupNorm(32, c)  # noqa: E731
+            elif norm_layer in ("batchnorm", "batchnorm2d", None):
+                norm = None
+            else:
+                raise ValueError(f"unknown norm_layer {norm_layer!r}")
+            backbone = getattr(torchvision.models, model_name)(norm_layer=norm, **kwargs)
+            old = backbone.conv1
+            backbone.conv1 = torch.nn.Conv2d(1, old.out_channels, old.kernel_size, old.stride, old.padding, bias=False)
+            features = backbone.fc.in_features
+            backbone.fc = torch.nn.Identity()
         self.backbone = backbone
         self.parameterization, self.convention = parameterization, convention
         self.xyz_regression = torch.nn.Linear(features, 3)
@@ -221,15 +227,22 @@ class TrainStep:
             offset += g.numel()
 
     # ------------------------------------------------------------------ the iteration
+    def _draw(self, itr):
+        """The random inputs of an iteration: (subject index, bone contrast, Euler angles in degrees (B,3),
+        translations (B,3)).  Subject and contrast come from the stream every rank shares, the poses from the
+        rank's own; tests replay recorded draws through this hook."""
+        subject = int(torch.randint(len(self.volumes), (1,), generator=self.shared_rng))
+        contrast = float(torch.empty(1).uniform_(1.0, 10.0, generator=self.shared_rng))
+        rot, xyz = random_pose_params(**self.pose_distribution, batch_size=self.local_batch, generator=self.pose_rng)
+        return subject, contrast, rot, xyz
+
     def step(self, itr):
         if self.use_cuda_graph:
             return self._step_graphed(itr)
         dev = self.device
-        subject = int(torch.randint(len(self.volumes), (1,), generator=self.shared_rng))
-        contrast = float(torch.empty(1).uniform_(1.0, 10.0, generator=self.shared_rng))
+        subject, contrast, rot, xyz = self._draw(itr)
         vol, seg, affinv, offset = self.volumes[subject]
 
-        rot, xyz = random_pose_params(**self.pose_distribution, batch_size=self.local_batch, generator=self.pose_rng)
         pose = convert(rot.to(dev), xyz.to(dev), parameterization="euler_angles", convention="ZXY", degrees=True)
         pose = pose.compose(offset)
 
@@ -256,6 +269,7 @@ class TrainStep:
         if self.world > 1:
             dist.all_reduce(sums, op=dist.ReduceOp.SUM)
         means = (sums / kept.clamp_min(1.0)).tolist()
+        means[0] /= self.n_grad_accum_itrs  # the reference logs the loss after dividing it for accumulation
         log.update(dict(zip(("loss", "mncc", "dgeo", "rgeo", "tgeo", "dice"), means)))
 
         if (itr + 1) % self.n_grad_accum_itrs == 0 or (itr + 1) == self.n_total_itrs:
@@ -324,7 +338,9 @@ class TrainStep:
             sums = torch.stack([(v.detach() * w).sum() for v in (loss, mncc, dgeo, rgeo, tgeo, dice)])
             if self.world > 1:
                 dist.all_reduce(sums, op=dist.ReduceOp.SUM)
-            self._log.copy_(torch.cat([sums / denom, kept / self.batch_size]))
+            means = sums / denom
+            means[0] /= self.n_grad_accum_itrs  # the reference logs the loss after dividing it for accumulation
+            self._log.copy_(torch.cat([means, kept / self.batch_size]))
 
     def _device_optimizer_step(self):
         self._allreduce_grads()
@@ -382,9 +398,7 @@ class TrainStep:
         return graph
 
     def _step_graphed(self, itr):
-        subject = int(torch.randint(len(self.volumes), (1,), generator=self.shared_rng))
-        contrast = float(torch.empty(1).uniform_(1.0, 10.0, generator=self.shared_rng))
-        rot, xyz = random_pose_params(**self.pose_distribution, batch_size=self.local_batch, generator=self.pose_rng)
+        subject, contrast, rot, xyz = self._draw(itr)
         slot = itr % len(self._stage)
         rot_h, xyz_h, ev = self._stage[slot]
         if self._stage_used[slot]:
