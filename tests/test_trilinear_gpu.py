@@ -219,9 +219,20 @@ def test_pose_gradients_smooth_volume_tight(cuda, monkeypatch, fused):
     assert rel_l2(x1.grad, x2.grad) < 2e-4
 
 
-@pytest.mark.parametrize("n,h,b", [(24, 16, 3), (40, 33, 2)])
-def test_volume_gradient_matches_oracle_and_is_deterministic(cuda, n, h, b):
-    """dL/dvolume (gather form, atomics-free) vs autograd through grid_sample's atomicAdd scatter."""
+@pytest.fixture
+def volgrad_version(request):
+    from xvr_b200._lib import call
+
+    call("xvr_set_volgrad_version", request.param)
+    yield request.param
+    call("xvr_set_volgrad_version", 1)
+
+
+@pytest.mark.parametrize("volgrad_version", [1, 2], indirect=True)
+@pytest.mark.parametrize("n,h,b", [(24, 16, 3), (40, 33, 2), (50, 64, 2)])
+def test_volume_gradient_matches_oracle_and_is_deterministic(cuda, n, h, b, volgrad_version):
+    """dL/dvolume (atomics-free: voxel-centric gather, or the experimental brick-local scatter) vs autograd through
+    grid_sample's atomicAdd scatter."""
     import oracle
 
     drr = make_drr(n, h)
