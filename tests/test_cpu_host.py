@@ -248,3 +248,45 @@ def test_evaluator_metrics():
     assert mtre == pytest.approx(3.0, abs=1e-3)
     assert 3.0 < mpe < 3.0 * 1020.0 / 700.0  # magnified by sdd / depth, depth in (700, 900) for these fiducials
     assert mrpe > 0 and dgeo == pytest.approx(3.0, abs=1e-3)
+
+
+def test_compat_package_serves_every_diffdrr_import_of_xvr(monkeypatch):
+    """Every ``from diffdrr.<module> import <name>`` statement in xvr's sources (listed from /root/reference/src and
+    /root/reference/scripts) resolves through the alias package xvr_b200/compat/diffdrr."""
+    import importlib
+    import os
+    import sys
+
+    import xvr_b200.compat
+
+    monkeypatch.syspath_prepend(os.path.dirname(xvr_b200.compat.__file__))
+    for name in [m for m in sys.modules if m == "diffdrr" or m.startswith("diffdrr.")]:
+        monkeypatch.delitem(sys.modules, name)
+    wanted = {
+        "diffdrr.drr": ["DRR"],
+        "diffdrr.pose": ["RigidTransform", "convert", "make_matrix"],
+        "diffdrr.registration": ["Registration", "N_ANGULAR_COMPONENTS"],
+        "diffdrr.metrics": ["DoubleGeodesicSE3", "MultiscaleNormalizedCrossCorrelation2d",
+                            "GradientNormalizedCrossCorrelation2d"],
+        "diffdrr.data": ["read", "load_example_ct", "transform_hu_to_density"],
+        "diffdrr.utils": ["resample"],
+        "diffdrr.visualization": ["plot_drr", "plot_mask"],
+    }
+    for module, names in wanted.items():
+        mod = importlib.import_module(module)
+        for n in names:
+            assert hasattr(mod, n), f"{module}.{n}"
+    assert "xvr_b200" in importlib.import_module("diffdrr").__version__
+
+
+def test_resample_identity_and_shapes():
+    from xvr_b200.utils import resample
+
+    img = torch.rand(2, 1, 40, 36)
+    assert torch.equal(resample(img, 1020.0, 0.2), img)
+    for kw in (dict(new_focal_len=1200.0), dict(new_delx=0.3), dict(new_x0=4.0, new_y0=-2.0), dict(new_delx=0.15)):
+        out = resample(img, 1020.0, 0.2, 0.0, 0.0, **kw)
+        assert out.shape == img.shape and torch.isfinite(out).all()
+    # doubling the pixel size shows the old image, shrunk, in the centre: the border is padding
+    big = resample(torch.ones(1, 1, 40, 40), 1020.0, 0.2, new_delx=0.4)
+    assert big[0, 0, 20, 20] > 0.99 and big[0, 0, 2, 2] == 0

@@ -7,7 +7,7 @@ The package mirrors the slice of ``diffdrr`` that xvr's training and registratio
 the C-ABI of ``include/xvr_b200.h`` (``libxvr_b200.so``); there is no CPU or PyTorch fallback.
 """
 
-from . import data, drr, metrics, pose, registration, renderers  # noqa: F401
+from . import data, drr, metrics, pose, registration, renderers, utils, visualization  # noqa: F401
 from .data import read, transform_hu_to_density  # noqa: F401
 from .drr import DRR, Detector  # noqa: F401
 from .pose import RigidTransform, convert, make_matrix  # noqa: F401

@@ -9,10 +9,10 @@ registrar/base.py:7-11, model/sampler.py:2, ...) bind to the B200 kernels withou
 import sys
 
 import xvr_b200
-from xvr_b200 import data, drr, metrics, pose, registration, renderers
+from xvr_b200 import data, drr, metrics, pose, registration, renderers, utils, visualization
 
 __version__ = "0.6.0+xvr_b200." + xvr_b200.__version__
 
 for _name, _mod in dict(data=data, drr=drr, metrics=metrics, pose=pose, registration=registration,
-                        renderers=renderers).items():
+                        renderers=renderers, utils=utils, visualization=visualization).items():
     sys.modules[f"{__name__}.{_name}"] = _mod

@@ -14,7 +14,7 @@ import torch
 
 from . import _conventions as conv
 
-__all__ = ["Volume", "Subject", "read", "transform_hu_to_density", "synthetic_ct", "REORIENT"]
+__all__ = ["Volume", "Subject", "read", "load_example_ct", "transform_hu_to_density", "synthetic_ct", "REORIENT"]
 
 REORIENT = {
     "AP": [[1.0, 0, 0, 0], [0, 0, -1.0, 0], [0, 1.0, 0, 0], [0, 0, 0, 1.0]],
@@ -156,6 +156,13 @@ def read(volume, labelmap=None, labels=None, orientation="AP", bone_attenuation_
         raise ValueError(f"Unrecognized orientation {orientation!r}")
     return Subject(vol, mask=mask, density=density, reorient=torch.tensor(REORIENT[orientation]),
                    orientation=orientation, fiducials=fiducials)
+
+
+def load_example_ct(*args, **kwargs):
+    """``diffdrr.data.load_example_ct`` downloads nothing here: the example CT ships with the DiffDRR wheel, which is
+    not part of this package (xvr only uses it as a placeholder subject for multi-subject training,
+    /root/reference/src/xvr/model/utils.py:155).  Use ``read(...)`` on your own volume or ``synthetic_ct``."""
+    raise RuntimeError("xvr_b200 does not bundle DiffDRR's example CT; pass a volume to read() or use synthetic_ct()")
 
 
 def synthetic_ct(n, seed=0, with_labels=False, device="cpu"):
