@@ -290,3 +290,48 @@ def test_resample_identity_and_shapes():
     # doubling the pixel size shows the old image, shrunk, in the centre: the border is padding
     big = resample(torch.ones(1, 1, 40, 40), 1020.0, 0.2, new_delx=0.4)
     assert big[0, 0, 20, 20] > 0.99 and big[0, 0, 2, 2] == 0
+
+
+@pytest.mark.parametrize("renderer", ["trilinear", "siddon"])
+def test_empty_batches_return_empty_results_without_a_launch(monkeypatch, renderer):
+    """Empty in -> empty out on every renderer / similarity entry, forward and backward (xvr indexes its batch with a
+    `keep` mask that can be all-False, /root/reference/src/xvr/model/trainer.py:202-204).  Host logic only: the
+    device check is lifted and any C-ABI call fails the test."""
+    from tests._scene import pixel_size
+    from xvr_b200 import drr as drr_mod
+    from xvr_b200 import metrics, renderers
+
+    def no_launch(name, *args):
+        raise AssertionError(f"{name} launched for an empty batch")
+
+    for mod in (renderers, drr_mod, metrics):
+        monkeypatch.setattr(mod, "cuda_f32", lambda t, what: t.to(torch.float32).contiguous())
+        monkeypatch.setattr(mod, "call", no_launch)
+        monkeypatch.setattr(mod, "stream", lambda: None)
+    monkeypatch.setattr(renderers._VolumeTexture, "get", lambda self, volume: None)
+
+    hu, _, affine = synthetic_ct(16)
+    drr = xvr_b200.DRR(read(hu, affine=affine), 1020.0, 8, pixel_size(8), renderer=renderer, reverse_x_axis=False)
+    rot = torch.zeros(0, 3, requires_grad=True)
+    xyz = torch.zeros(0, 3, requires_grad=True)
+    pose = xvr_b200.convert(rot, xyz, parameterization="euler_angles", convention="ZXY")
+    img = drr(pose)
+    assert img.shape == (0, 1, 8, 8)
+    img.sum().backward()
+    assert rot.grad.shape == (0, 3) and xyz.grad.shape == (0, 3)
+    assert drr(rot, xyz, parameterization="euler_angles", convention="ZXY").shape == (0, 1, 8, 8)
+    with torch.no_grad():
+        source, target = drr.detector(pose, None)
+        raylen = (target - source).norm(dim=-1).unsqueeze(1)
+        assert drr.renderer(drr.density, drr.affine_inverse(source), drr.affine_inverse(target),
+                            raylen).shape == (0, 1, 64)
+        assert drr.renderer(drr.density, torch.zeros(2, 1, 3), torch.zeros(2, 0, 3),
+                            torch.zeros(2, 1, 0)).shape == (2, 1, 0)
+
+    x = torch.zeros(0, 1, 32, 32, requires_grad=True)
+    y = torch.zeros(0, 1, 32, 32)
+    s1 = metrics.MultiscaleNormalizedCrossCorrelation2d([None, 9], [0.5, 0.5])(x, y)
+    s2 = metrics.GradientNormalizedCrossCorrelation2d(11, sigma=0.0)(x, y)
+    assert s1.shape == s2.shape == (0,)
+    (s1.sum() + s2.sum()).backward()
+    assert x.grad.shape == x.shape

@@ -41,7 +41,8 @@ class _EulerCamera(torch.autograd.Function):
         cam2vox = torch.empty(B, 3, 4, device=rot.device, dtype=torch.float32)
         ctx.consts = ((ctypes.c_int * 3)(*axes), int(conv.CONVERT_TRANSLATION_IN_ROTATED_FRAME),
                       (ctypes.c_float * 16)(*reorient16), (ctypes.c_float * 16)(*affinv16))
-        call("xvr_euler_camera_fwd", ptr(rot), ptr(xyz), B, *ctx.consts, ptr(cam2world), ptr(cam2vox), stream())
+        if B > 0:
+            call("xvr_euler_camera_fwd", ptr(rot), ptr(xyz), B, *ctx.consts, ptr(cam2world), ptr(cam2vox), stream())
         ctx.save_for_backward(rot, xyz)
         ctx.mark_non_differentiable(cam2world)  # only feeds the ray length, which a rigid motion leaves unchanged
         return cam2vox, cam2world
@@ -51,6 +52,8 @@ class _EulerCamera(torch.autograd.Function):
         rot, xyz = ctx.saved_tensors
         B = rot.shape[0]
         grot, gxyz = torch.empty_like(rot), torch.empty_like(xyz)
+        if B == 0:
+            return grot, gxyz, None, None, None
         call("xvr_euler_camera_bwd", ptr(rot), ptr(xyz), B, *ctx.consts, ptr(cuda_f32(g_cam2vox, "grad")), ptr(grot),
              ptr(gxyz), stream())
         return grot, gxyz, None, None, None
@@ -182,7 +185,8 @@ class DRR(torch.nn.Module):
 
     def reshape_transform(self, img, batch_size):
         if self.reshape:
-            return img.view(batch_size, -1, self.detector.height, self.detector.width)
+            # (B, C, H*W) -> (B, C, H, W); the channel count is spelled out so that an empty batch reshapes too
+            return img.view(batch_size, img.shape[1], self.detector.height, self.detector.width)
         return img
 
     # ------------------------------------------------------------------ rendering

@@ -38,6 +38,9 @@ class _MultiNCC(torch.autograd.Function):
             raise ValueError(f"expected two (B,C,H,W) images of equal shape; got {tuple(x1.shape)}, {tuple(x2.shape)}")
         B, C, H, W = x1.shape
         score = torch.empty(B, device=x1.device, dtype=torch.float32)
+        if B == 0:  # empty batch -> empty score vector (the reference's mean over dims 1.. of an empty batch)
+            ctx.cfg = None
+            return score
         tiles = max(((H + _NCC_T - 1) // _NCC_T) * ((W + _NCC_T - 1) // _NCC_T), 6)
         work = torch.empty(B * C * tiles, device=x1.device, dtype=torch.float32)
         g1, g2 = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
@@ -54,6 +57,8 @@ class _MultiNCC(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gscore):
+        if ctx.cfg is None:
+            return None, None, None, None, None
         x1, x2, *saved = ctx.saved_tensors
         patches, weights = ctx.cfg
         B, C, H, W = x1.shape
@@ -79,7 +84,8 @@ class _Sobel(torch.autograd.Function):
             raise ValueError(f"Sobel expects (B,1,H,W); got {tuple(x.shape)}")
         B, _, H, W = x.shape
         out = torch.empty(B, 2, H, W, device=x.device, dtype=torch.float32)
-        call("xvr_sobel_fwd", ptr(x), B, H, W, ptr(out), stream())
+        if B > 0:
+            call("xvr_sobel_fwd", ptr(x), B, H, W, ptr(out), stream())
         return out
 
     @staticmethod
@@ -87,7 +93,8 @@ class _Sobel(torch.autograd.Function):
         gout = cuda_f32(gout, "grad_output")
         B, _, H, W = gout.shape
         gx = torch.empty(B, 1, H, W, device=gout.device, dtype=torch.float32)
-        call("xvr_sobel_bwd", ptr(gout), B, H, W, ptr(gx), stream())
+        if B > 0:
+            call("xvr_sobel_bwd", ptr(gout), B, H, W, ptr(gx), stream())
         return gx
 
 

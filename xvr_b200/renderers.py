@@ -140,6 +140,9 @@ class _RenderRays(torch.autograd.Function):
         det_h, det_w = det_hw if det_hw is not None and det_hw[0] * det_hw[1] == N else (0, 0)
         need_pose_grad = any(ctx.needs_input_grad[1:4])
         out = torch.empty(B, C, N, device=volume.device, dtype=torch.float32)
+        ctx.empty = B == 0 or N == 0
+        if ctx.empty:  # empty in -> empty out, as grid_sample does; nothing to launch
+            return out
         # with label channels the Jacobian is the one of the channel SUM: enough whenever the caller collapses the
         # channels (trainer.py:294 img.sum(dim=1)); backward() falls back to the recompute kernel otherwise
         jac = torch.empty(B, 7, N, device=volume.device, dtype=torch.float32) if need_pose_grad else None
@@ -163,6 +166,8 @@ class _RenderRays(torch.autograd.Function):
         gsource = torch.empty(B, 1, 3, device=dev, dtype=torch.float32)
         gtarget = torch.empty(B, N, 3, device=dev, dtype=torch.float32)
         graylen = torch.empty(B, 1, N, device=dev, dtype=torch.float32)
+        if ctx.empty:
+            return None, gsource.zero_(), gtarget, graylen, None, None, None, None, None, None
         work = torch.empty(B, 3, N, device=dev, dtype=torch.float32)
         jac = ctx.saved_tensors[0]
         # One upstream gradient per ray: single channel, or every channel sees the same gradient -- autograd hands
@@ -190,6 +195,10 @@ class _RenderDRR(torch.autograd.Function):
         out = torch.empty(B, 1, H * W, device=volume.device, dtype=torch.float32)
         jac = torch.empty(B, 7, H * W, device=volume.device, dtype=torch.float32) if ctx.needs_input_grad[1] else None
         det = (ctypes.c_float * 9)(*det9)
+        ctx.det = (det, B, H, W, args, tuple(volume.shape))
+        if B == 0:  # an empty pose batch renders to an empty image batch; nothing to launch
+            ctx.save_for_backward(jac)
+            return out
         call("xvr_trilinear_drr_fwd", ptr(volume), voltex, *volume.shape, ptr(cam2vox), ptr(cam2world), det, B, H, W,
              *args, lw, cw, ptr(out), ptr(jac), stream())
         ctx.det = (det, B, H, W, args, tuple(volume.shape))
@@ -202,6 +211,10 @@ class _RenderDRR(torch.autograd.Function):
         det, B, H, W, args, shape = ctx.det
         gout = cuda_f32(gout, "grad_output")
         gG = gvol = None
+        if B == 0:
+            return (torch.zeros(shape, device=gout.device) if ctx.needs_input_grad[0] else None,
+                    torch.zeros(0, 3, 4, device=gout.device) if ctx.needs_input_grad[1] else None,
+                    None, None, None, None, None)
         if ctx.needs_input_grad[1]:
             gG = torch.empty(B, 3, 4, device=gout.device, dtype=torch.float32)
             slices = _lib.lib().xvr_drr_jac_bwd_slices(B, H * W)
