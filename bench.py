@@ -150,8 +150,13 @@ def cpu_reference_step(density, affinv, reorient, rot, xyz, rows, det, gout):
     return img.detach(), rot.grad, xyz.grad
 
 
-def cpu_reference(steps, warmup, vol_n=VOL_N, det=DET, target_seconds=8.0):
-    """Time the reference's CPU path on this box's host cores on a bounded sample of the workload."""
+def cpu_reference(steps, warmup, vol_n=VOL_N, det=DET, min_seconds=0.0, max_seconds=120.0):
+    """Time the reference's CPU path on this box's host cores on a bounded sample of the workload.
+
+    One step = `b` poses x 8 of the detector's rows (fwd + bwd w.r.t. the pose through autograd).  `steps` timed
+    steps are run after `warmup` untimed ones; the count is raised until `min_seconds` of CPU work have been timed
+    (the in-line `cpu_baseline` of the main arm asks for ~12 s) and cut so that the timed region stays under
+    `max_seconds` (the `--impl reference` arm must end within a few minutes whatever --steps says)."""
     import numpy as np
 
     from xvr_b200.data import REORIENT, read, synthetic_ct
@@ -169,19 +174,23 @@ def cpu_reference(steps, warmup, vol_n=VOL_N, det=DET, target_seconds=8.0):
     n_rows = max(1, det // 32)
     rows = torch.arange(0, det, det // n_rows)[:n_rows]
     gout = torch.rand(b, 1, len(rows) * det, generator=torch.Generator().manual_seed(1))
+    for _ in range(max(warmup, 1)):
+        cpu_reference_step(density, affinv, reorient, rot, xyz, rows, det, gout)
     times = []
-    for i in range(warmup + steps):
+    while True:
         t0 = time.perf_counter()
         cpu_reference_step(density, affinv, reorient, rot, xyz, rows, det, gout)
-        dt = time.perf_counter() - t0
-        if i >= warmup:
-            times.append(dt)
+        times.append(time.perf_counter() - t0)
+        t = sum(times)
+        per = t / len(times)
+        if t + per > max_seconds or (len(times) >= steps and t >= min_seconds):
+            break
     drr_equiv = b * len(rows) / det
-    t = sum(times)
-    sample = (f"{b} poses x {len(rows)} of {det} detector rows ({len(rows) * det} rays each, {N_POINTS} samples/ray) "
-              f"of the {vol_n}^3 volume per step = {drr_equiv:.3f} DRR-equivalents; fwd+bwd(pose) through autograd")
+    sample = (f"{len(times)} steps of {b} poses x {len(rows)} of {det} detector rows ({len(rows) * det} rays each, "
+              f"{N_POINTS} samples/ray) of the {vol_n}^3 volume = {drr_equiv:.3f} DRR-equivalents per step, "
+              f"{t:.1f} s of CPU work; fwd+bwd(pose) through autograd")
     return {"value": drr_equiv * len(times) / t, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
-            "seconds_per_step": t / len(times)}
+            "seconds_per_step": t / len(times), "steps": len(times)}
 
 
 # ------------------------------------------------------------------------------------------ main
@@ -213,8 +222,9 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        steps, warmup = max(1, min(args.steps, 3)), min(args.warmup, 1)
-        res = cpu_reference(steps, warmup, args.vol, args.det)
+        warmup = max(1, min(args.warmup, 2))
+        res = cpu_reference(max(1, args.steps), warmup, args.vol, args.det, min_seconds=0.0, max_seconds=120.0)
+        steps = res["steps"]
         line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
                 "steps": steps, "warmup": warmup, "ms_per_step": res["seconds_per_step"] * 1e3,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -353,7 +363,7 @@ def main():
             "kernel_share_of_step": step_share,
         }
         if world == 1 and not args.no_cpu_baseline:
-            res = cpu_reference(1, 1, args.vol, args.det)
+            res = cpu_reference(1, 1, args.vol, args.det, min_seconds=12.0, max_seconds=30.0)
             line["cpu_baseline"] = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
         print(json.dumps(line))
     if world > 1:
