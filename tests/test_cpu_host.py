@@ -335,3 +335,52 @@ def test_empty_batches_return_empty_results_without_a_launch(monkeypatch, render
     assert s1.shape == s2.shape == (0,)
     (s1.sum() + s2.sum()).backward()
     assert x.grad.shape == x.shape
+
+
+def test_checkpoint_round_trip_and_pose_prediction(tmp_path):
+    """*.pth files carry the reference's keys (trainer.py:318-332), load_model rebuilds the regressor from the
+    stored config (network.py:57-78) and predict_pose resamples / crops / normalises as inference.py:9-39."""
+    from xvr_b200.inference import construct_antipode, correct_pose, load_model, predict_pose, save_checkpoint
+    from xvr_b200.trainer import PoseRegressor, WarmupCosineSchedule
+
+    torch.manual_seed(0)
+    model = PoseRegressor("resnet18", "quaternion_adjugate", "ZXY", height=64, unit_conversion_factor=1000.0).eval()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    sched = WarmupCosineSchedule(opt, 10, 100)
+    config = dict(model_name="resnet18", parameterization="quaternion_adjugate", convention="ZXY",
+                  norm_layer="groupnorm", height=64, sdd=1020.0, delx=4.0, unit_conversion_factor=1000.0)
+    path = save_checkpoint(tmp_path / "0000.pth", model, opt, sched, itr=7, model_number=0, config=config)
+    ckpt = torch.load(path, weights_only=False)
+    assert set(ckpt) == {"model_state_dict", "optimizer_state_dict", "scheduler_state_dict", "itr", "model_number",
+                         "date", "config"}
+    assert ckpt["itr"] == 7 and ckpt["config"]["height"] == 64
+    # timm's ResNet parameter names (what an xvr-written model_state_dict holds)
+    keys = set(ckpt["model_state_dict"])
+    assert {"backbone.conv1.weight", "backbone.bn1.weight", "backbone.layer2.0.downsample.0.weight",
+            "backbone.layer4.1.bn2.bias", "xyz_regression.weight", "rot_regression.bias"} <= keys
+    assert not any(k.startswith("backbone.fc") for k in keys)
+
+    loaded, cfg, date = load_model(path, meta=True, device="cpu")
+    assert not loaded.training and cfg == config and date is not None
+    img = torch.rand(2, 1, 120, 150)
+    pose_a, seen = predict_pose(model, config, img, 1020.0, 2.0, 2.0, 0.0, 0.0)
+    pose_b, _ = predict_pose(loaded, cfg, img, 1020.0, 2.0, 2.0, 0.0, 0.0)
+    assert seen.shape == (2, 1, 64, 64)
+    assert torch.equal(pose_a.matrix, pose_b.matrix)
+    with pytest.raises(AssertionError):
+        predict_pose(model, config, img, 1020.0, 2.0, 2.5, 0.0, 0.0)
+
+    # models saved before the unit switch have no unit_conversion_factor: the reference falls back to 1.0
+    old = {k: v for k, v in config.items() if k != "unit_conversion_factor"}
+    save_checkpoint(tmp_path / "old.pth", model, opt, sched, 0, 0, old)
+    assert load_model(tmp_path / "old.pth", device="cpu")[0].unit_conversion_factor == 1.0
+
+    anti = construct_antipode(pose_a)
+    r0, _ = pose_a.convert("euler_angles", "ZXY")
+    r1, _ = anti.convert("euler_angles", "ZXY")
+    assert torch.allclose(r1[:, 1:], r0[:, 1:] * torch.tensor([-1.0, 1.0]), atol=1e-4)
+    assert torch.allclose(construct_antipode(anti).matrix, pose_a.matrix, atol=5e-3)
+    assert correct_pose(pose_a, None) is pose_a
+    shift = xvr_b200.convert(torch.zeros(1, 3), torch.tensor([[1.0, 2.0, 3.0]]), parameterization="euler_angles",
+                             convention="ZXY")
+    assert torch.allclose(correct_pose(pose_a, shift.matrix[0]).matrix, pose_a.compose(shift).matrix)

@@ -281,6 +281,14 @@ class TrainStep:
         log["lr"] = self.scheduler.get_last_lr()[0]
         return log
 
+    def checkpoint(self, path, itr, config, model_number=0):
+        """Write a ``*.pth`` with the reference's keys (trainer.py:318-332); rank 0 only, every rank may call it."""
+        from .inference import save_checkpoint  # noqa: PLC0415
+
+        if self.rank == 0:
+            save_checkpoint(path, self.model, self.optimizer, self.scheduler, itr, model_number, config)
+        return path
+
     # ------------------------------------------------------------------ the iteration as CUDA graphs
     # The eager iteration above costs ~20 ms of host time (a ResNet forward/backward, two renders, ~10^3 small
     # launches and five host round trips), more than its GPU time -- and at 8 ranks the GPU share shrinks 8x while
