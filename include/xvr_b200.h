@@ -79,8 +79,8 @@ int xvr_trilinear_drr_bwd_volume(const float* cam2vox, const float* vox2cam, con
                                  const float* det9, int B, int det_h, int det_w, int n_points, int step_mode,
                                  float eps, const float* gout, int D0, int D1, int D2, float* workspace, float* gvol,
                                  int accumulate, void* stream);
-/* test / tuning hook: 1 = voxel-centric gather (default), 2 = brick-local scatter in shared memory (experimental:
- * same result, no atomics, deterministic; csrc/volgrad.cu) */
+/* formulation of the volume gradient: 2 = brick-local scatter in shared memory (default), 1 = voxel-centric gather
+ * (independent cross-check); both atomics-free and deterministic, same result (csrc/volgrad.cu) */
 int xvr_set_volgrad_version(int version);
 
 /* ---- Siddon renderer = diffdrr.renderers.Siddon.forward (same call sites, --renderer siddon)

@@ -93,7 +93,7 @@ def section_trilinear():
     def volgrad():
         vol.grad = None
         img.backward(gout[:Bv].view_as(img), retain_graph=True)
-    report("trilinear dL/dvolume (gather form, atomics-free)", timeit(volgrad, reps=2, warm=1), Bv * 256 * 256 * 500 * 64, Bv, "DRR/s", "A_bwd_vol = 64 B/sample")
+    report("trilinear dL/dvolume (brick-local scatter, atomics-free)", timeit(volgrad, reps=2, warm=1), Bv * 256 * 256 * 500 * 64, Bv, "DRR/s", "A_bwd_vol = 64 B/sample")
     drr.density = keep
     del vol, img, drr
 

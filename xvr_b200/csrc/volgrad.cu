@@ -75,21 +75,51 @@ __global__ void __launch_bounds__(256) volume_grad_kernel(const VolGradParams p)
       for (int c = 0; c < 3; ++c) row[a][c] = __ldg(Gi + a * 4 + c);
       q[a] = fmaf(row[a][2], pv[2], fmaf(row[a][1], pv[1], fmaf(row[a][0], pv[0], __ldg(Gi + a * 4 + 3))));
     }
-    if (!(q[2] > 1e-3f)) continue;  // behind the source
-    const float m = sdd / q[2];
-    // continuous pixel coordinates of the voxel centre and the half-extent of its +-1 voxel support
-    const float cj = (q[0] * m - p.geom.o[0]) * inv_vx;
-    const float ci = (q[1] * m - p.geom.o[1]) * inv_uy;
-    float rj = 0.f, ri = 0.f;
+    // Candidate rays = pixel window of the voxel's +-1 support.  rz is the depth half-extent of that support.
+    const float rz = fabsf(row[2][0]) + fabsf(row[2][1]) + fabsf(row[2][2]);
+    int j0 = 0, j1 = p.W - 1, i0 = 0, i1 = p.H - 1;
+    if (q[2] > 8.f * rz) {
+      // far from the source plane: window from the projection linearised at the voxel centre, padded by 1 %
+      const float m = sdd / q[2];
+      const float cj = (q[0] * m - p.geom.o[0]) * inv_vx;
+      const float ci = (q[1] * m - p.geom.o[1]) * inv_uy;
+      float rj = 0.f, ri = 0.f;
 #pragma unroll
-    for (int a = 0; a < 3; ++a) {
-      rj += fabsf(row[0][a] - (q[0] / q[2]) * row[2][a]);
-      ri += fabsf(row[1][a] - (q[1] / q[2]) * row[2][a]);
+      for (int a = 0; a < 3; ++a) {
+        rj += fabsf(row[0][a] - (q[0] / q[2]) * row[2][a]);
+        ri += fabsf(row[1][a] - (q[1] / q[2]) * row[2][a]);
+      }
+      rj = rj * m * fabsf(inv_vx) * 1.01f + 1e-3f;
+      ri = ri * m * fabsf(inv_uy) * 1.01f + 1e-3f;
+      j0 = max(0, (int)ceilf(cj - rj)); j1 = min(p.W - 1, (int)floorf(cj + rj));
+      i0 = max(0, (int)ceilf(ci - ri)); i1 = min(p.H - 1, (int)floorf(ci + ri));
+    } else {
+      // near the source (a source inside or next to the volume) the linearisation is no bound: take the pixel box of
+      // the 8 projected corners of the support (a convex set in front of the source projects inside the box of its
+      // projected vertices); a support that reaches the source plane has no finite window -- every ray is a
+      // candidate -- and one entirely behind the source is never reached.
+      float jmin = INFINITY, jmax = -INFINITY, imin = INFINITY, imax = -INFINITY;
+      int in_front = 0;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const float sx = (c & 1) ? 1.f : -1.f, sy = (c & 2) ? 1.f : -1.f, sz = (c & 4) ? 1.f : -1.f;
+        const float q0 = q[0] + sx * row[0][0] + sy * row[0][1] + sz * row[0][2];
+        const float q1 = q[1] + sx * row[1][0] + sy * row[1][1] + sz * row[1][2];
+        const float q2 = q[2] + sx * row[2][0] + sy * row[2][1] + sz * row[2][2];
+        if (q2 > 1e-3f * sdd) {
+          const float m = sdd / q2;
+          const float cj = (q0 * m - p.geom.o[0]) * inv_vx, ci = (q1 * m - p.geom.o[1]) * inv_uy;
+          jmin = fminf(jmin, cj); jmax = fmaxf(jmax, cj);
+          imin = fminf(imin, ci); imax = fmaxf(imax, ci);
+          ++in_front;
+        }
+      }
+      if (in_front == 0) continue;  // behind the source
+      if (in_front == 8) {
+        j0 = max(0, (int)ceilf(jmin - 1e-3f)); j1 = min(p.W - 1, (int)floorf(jmax + 1e-3f));
+        i0 = max(0, (int)ceilf(imin - 1e-3f)); i1 = min(p.H - 1, (int)floorf(imax + 1e-3f));
+      }
     }
-    rj = rj * m * fabsf(inv_vx) * 1.01f + 1e-3f;
-    ri = ri * m * fabsf(inv_uy) * 1.01f + 1e-3f;
-    const int j0 = max(0, (int)ceilf(cj - rj)), j1 = min(p.W - 1, (int)floorf(cj + rj));
-    const int i0 = max(0, (int)ceilf(ci - ri)), i1 = min(p.H - 1, (int)floorf(ci + ri));
     if (i0 > i1 || j0 > j1) continue;
     // the source is the translation column of cam2vox (what generate_ray uses)
     const float* G = p.geom.cam2vox + b * 12;
@@ -133,9 +163,10 @@ __global__ void __launch_bounds__(256) volume_grad_kernel(const VolGradParams p)
 
 
 // ------------------------------------------------------------------------------------------------------------------
-// Version 2 (selected with xvr_set_volgrad_version(2); version 1 above stays the default for one more round):
-// brick-local scatter, no atomics, deterministic.  Passes the same oracle-parity / determinism tests as version 1,
-// agrees with it to 8e-8 relative L2 at config-2 scale and is 1.7x faster there (12.2 vs 21.0 ms per 8 poses).
+// Version 2 (the default; xvr_set_volgrad_version(1) selects the gather above as an independent cross-check):
+// brick-local scatter, no atomics, deterministic.  Passes the oracle-parity / determinism tests including
+// anisotropic voxels, a shifted / reversed / non-square detector and a source inside the volume, agrees with
+// version 1 to 8e-8 relative L2 at config-2 scale and is 1.7x faster there (12.2 vs 21.0 ms per 8 poses).
 //
 // A warp owns a 16^3 brick of the gradient volume in shared memory.  For every pose it projects the brick (grown by
 // the one-voxel support of the trilinear hat) onto the detector, walks the rays of that pixel window and
@@ -305,7 +336,7 @@ __global__ void __launch_bounds__(32) volume_grad_brick_kernel(const VolGradPara
   }
 }
 
-static int g_volgrad_version = 1;
+static int g_volgrad_version = 2;
 
 }  // namespace xvr
 
@@ -356,7 +387,7 @@ extern "C" int xvr_trilinear_drr_bwd_volume(const float* cam2vox, const float* v
   return check_launch("xvr_trilinear_drr_bwd_volume");
 }
 
-// Test / tuning hook: 1 = voxel-centric gather (default), 2 = brick-local scatter (experimental, see above).
+// Selects the formulation: 2 = brick-local scatter (default), 1 = voxel-centric gather (kept as the cross-check).
 extern "C" int xvr_set_volgrad_version(int version) {
   if (version != 1 && version != 2) {
     set_last_error("xvr_set_volgrad_version: expected 1 or 2");
