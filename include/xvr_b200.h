@@ -120,6 +120,19 @@ int xvr_ncc_bwd(const float* x1, const float* x2, const float* coef, int which, 
 int xvr_sobel_fwd(const float* x, int B, int H, int W, float* out /* (B,2,H,W) */, void* stream);
 int xvr_sobel_bwd(const float* gout, int B, int H, int W, float* gx /* (B,1,H,W) */, void* stream);
 
+/* ---- Value and gradient of the registration similarity in nine launches: the chain
+ *   XrayTransforms(moving) -> beta * mNCC([None, p]) + (1 - beta) * GradNCC(q, sigma = 0) -> .sum() -> backward
+ * of /root/reference/src/xvr/registrar/base.py:245-252 (transform: utils/preprocess.py:5-29, no Equalize, no resize).
+ *   fixed (B,1,H,W) the transformed target, fixed_sobel (B,2,H,W) = xvr_sobel_fwd(fixed), moving (B,1,H,W) raw DRRs;
+ *   transform = (x - min x) / (max x - min x + std_eps) over the whole batch, then (. - mean) * inv_std;
+ *   score[0] = sum_b w_global NCC + w_patch NCC_p + w_grad NCC_q(Sobel);  grad (B,1,H,W) = d score / d moving;
+ *   workspace: xvr_regsim_workspace_floats(B, H, W, p, q) floats (-1 for invalid sizes). */
+long long xvr_regsim_workspace_floats(int B, int H, int W, int patch_mncc, int patch_gncc);
+int xvr_regsim(const float* fixed, const float* fixed_sobel, const float* moving, int B, int H, int W, float std_eps,
+               float mean, float inv_std, int patch_mncc, int patch_gncc, float w_global, float w_patch,
+               float w_grad, float ncc_eps, float* workspace, long long workspace_floats, float* score, float* grad,
+               void* stream);
+
 /* ---- The scalar ends of one registration iteration, one launch each (/root/reference/src/xvr/registrar/base.py:245-278).
  * xvr_euler_camera_*: convert(rot, xyz, "euler_angles", convention) -> reorient.compose(pose) -> affine inverse,
  *   i.e. the camera matrices the fused renderer consumes, and the matching backward.  rot, xyz (B,3) DEVICE;

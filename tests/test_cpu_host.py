@@ -58,6 +58,13 @@ def test_invalid_arguments_return_error_codes_not_crashes():
     assert b"xvr_reduce_rows" in lib.xvr_last_error()
     assert lib.xvr_ncc_fwd(None, None, 1, 1, 8, 8, 0, 1e-5, 1.0, 0, None, None, None, None, None) == -1
     assert lib.xvr_volume_create(0, 4, 4, ctypes.byref(ctypes.c_void_p())) == -1
+    # fused registration similarity: sizes are validated (and the workspace sized) without touching the device
+    assert lib.xvr_regsim_workspace_floats(1, 8, 8, 9, 11) == -1  # patches larger than the image
+    n = lib.xvr_regsim_workspace_floats(1, 256, 256, 9, 11)
+    assert n >= 256 * 256 * (1 + 2 + 1 + 2) + 4 * 248 * 248 + 8 * 246 * 246
+    assert lib.xvr_regsim(None, None, None, 1, 256, 256, 1e-6, 0.15, 10.0, 9, 11, 0.25, 0.25, 0.5, 1e-5, None, n, None,
+                          None, None) == -1
+    assert b"xvr_regsim" in lib.xvr_last_error()
 
 
 def test_product_never_imports_the_oracle():

@@ -43,6 +43,9 @@ _SIGNATURES = {
     "xvr_ncc_bwd": ([P, P, P, c_int, P, c_int, c_int, c_int, c_int, c_int, c_float, c_int, P, P], c_int),
     "xvr_sobel_fwd": ([P, c_int, c_int, c_int, P, P], c_int),
     "xvr_sobel_bwd": ([P, c_int, c_int, c_int, P, P], c_int),
+    "xvr_regsim_workspace_floats": ([c_int, c_int, c_int, c_int, c_int], ctypes.c_longlong),
+    "xvr_regsim": ([P, P, P, c_int, c_int, c_int, c_float, c_float, c_float, c_int, c_int, c_float, c_float, c_float,
+                    c_float, P, ctypes.c_longlong, P, P, P], c_int),
     "xvr_hu_stats": ([P, ctypes.c_longlong, c_float, c_float, P, P, P], c_int),
     "xvr_hu_to_density": ([P, ctypes.c_longlong, c_float, c_float, c_float, P, P, P, P], c_int),
     "xvr_reduce_rows": ([P, c_int, c_int, P, P], c_int),

@@ -285,6 +285,174 @@ sobel_bwd_kernel(const float* __restrict__ gout, int H, int W, float* __restrict
   gx[(int64_t)blockIdx.z * H * W + py * W + px] = acc;
 }
 
+
+// ---------------------------------------------------------------------------------------------- registration similarity
+// One registration iteration scores  S = sum_b  w_g NCC(f, y) + w_p NCC_p(f, y) + w_s NCC_q(Sobel f, Sobel y)  with
+// y = XrayTransforms(x) = ((x - min x) / (max x - min x + e) - mean) / std  of the raw DRR batch x and a fixed,
+// already transformed X-ray f (/root/reference/src/xvr/registrar/base.py:245-252, utils/preprocess.py:5-29), and
+// immediately differentiates it.  Composed from tensor ops that is ~60 launches around six real kernels; the three
+// kernels below supply the ends (standardise + Sobel in, score out, standardise-backward out) so that the whole
+// value-and-gradient evaluation is nine launches.  They run as ONE CTA each: a registration batch is a single
+// 256 x 256 image (64 elements per thread), and a single CTA needs no second launch for its reductions.
+
+// Fixed-tree reductions over a 1024-thread CTA; every thread receives the result.
+template <typename T, typename Op>
+__device__ __forceinline__ T cta1024_reduce(T v, Op op, T* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = op(v, __shfl_xor_sync(0xffffffffu, v, o));
+  __syncthreads();  // red may still be read from the previous reduction
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  v = red[threadIdx.x & 31];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = op(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// stats = {min, max, #elements equal to min, #elements equal to max, max - min + e}; ones (B) <- 1;
+// y (B,1,H,W) <- XrayTransforms(x); sob (B,2,H,W) <- Sobel(y) with zero padding in y-space (conv2d padding=1).
+__global__ void __launch_bounds__(1024)
+regsim_prep_kernel(const float* __restrict__ x, int B, int H, int W, float std_eps, float mean, float inv_std,
+                   float* __restrict__ stats, float* __restrict__ ones, float* __restrict__ y,
+                   float* __restrict__ sob) {
+  __shared__ float redf[32];
+  __shared__ int redi[32];
+  const int tid = threadIdx.x;
+  const int HW = H * W, n = B * HW;
+  float lo = INFINITY, hi = -INFINITY;
+  for (int i = tid; i < n; i += 1024) {
+    const float v = __ldg(x + i);
+    lo = fminf(lo, v);
+    hi = fmaxf(hi, v);
+  }
+  lo = cta1024_reduce(lo, [](float a, float b) { return fminf(a, b); }, redf);
+  hi = cta1024_reduce(hi, [](float a, float b) { return fmaxf(a, b); }, redf);
+  int nlo = 0, nhi = 0;
+  for (int i = tid; i < n; i += 1024) {
+    const float v = __ldg(x + i);
+    nlo += v == lo;
+    nhi += v == hi;
+  }
+  nlo = cta1024_reduce(nlo, [](int a, int b) { return a + b; }, redi);
+  nhi = cta1024_reduce(nhi, [](int a, int b) { return a + b; }, redi);
+  const float r = (hi - lo) + std_eps;
+  if (tid == 0) {
+    stats[0] = lo;
+    stats[1] = hi;
+    stats[2] = (float)nlo;
+    stats[3] = (float)nhi;
+    stats[4] = r;
+  }
+  for (int b = tid; b < B; b += 1024) ones[b] = 1.f;
+  for (int i = tid; i < n; i += 1024) {
+    const int b = i / HW, rem = i - b * HW;
+    const int py = rem / W, px = rem - py * W;
+    const float* im = x + (int64_t)b * HW;
+    auto at = [&](int yy, int xx) -> float {
+      if (yy < 0 || yy >= H || xx < 0 || xx >= W) return 0.f;
+      return (__fdiv_rn(__ldg(im + yy * W + xx) - lo, r) - mean) * inv_std;
+    };
+    const float a = at(py - 1, px - 1), bb = at(py - 1, px), c = at(py - 1, px + 1);
+    const float d = at(py, px - 1), e = at(py, px), f = at(py, px + 1);
+    const float g = at(py + 1, px - 1), h = at(py + 1, px), k = at(py + 1, px + 1);
+    y[i] = e;
+    float* o = sob + (int64_t)b * 2 * HW + rem;
+    o[0] = (a - c) + 2.f * (d - f) + (g - k);
+    o[HW] = (a - g) + 2.f * (bb - h) + (c - k);
+  }
+}
+
+// score[0] = w_g sum_b NCC_b + w_p sum(partial_p) + w_s sum(partial_s)  (weights already hold the 1/count factors)
+__global__ void __launch_bounds__(1024)
+regsim_score_kernel(const float* __restrict__ gstat, int B, float w_g, const float* __restrict__ partial_p, int n_p,
+                    float w_p, const float* __restrict__ partial_s, int n_s, float w_s, float* __restrict__ score) {
+  __shared__ float redf[32];
+  const int tid = threadIdx.x;
+  float acc_g = 0.f, acc_p = 0.f, acc_s = 0.f;
+  for (int b = tid; b < B; b += 1024) acc_g += gstat[(int64_t)b * 6];
+  for (int i = tid; i < n_p; i += 1024) acc_p += partial_p[i];
+  for (int i = tid; i < n_s; i += 1024) acc_s += partial_s[i];
+  const float v = cta1024_reduce(w_g * acc_g + w_p * acc_p + w_s * acc_s, [](float a, float b) { return a + b; }, redf);
+  if (tid == 0) score[0] = v;
+}
+
+// g_y (B,1,H,W): dS/dy from the NCC terms on entry; Sobel^T of g_sob (B,2,H,W) is added, then the chain through
+// y = ((x - lo) / r - mean) * inv_std with lo = min x, r = max x - min x + e (the extrema receive their share evenly
+// over ties, as torch's min()/max() backward distributes it):
+//   dS/dx_j = a g_j + [x_j = lo] (c S1 - a S0) / n_lo - [x_j = hi] c S1 / n_hi,
+//   a = inv_std / r, c = inv_std / r^2, S0 = sum g, S1 = sum g (x - lo).
+__global__ void __launch_bounds__(1024)
+regsim_bwd_finish_kernel(const float* __restrict__ x, const float* __restrict__ g_sob, const float* __restrict__ stats,
+                         int B, int H, int W, float inv_std, float* __restrict__ g_y, float* __restrict__ grad) {
+  __shared__ float redf[32];
+  const int tid = threadIdx.x;
+  const int HW = H * W, n = B * HW;
+  const float lo = stats[0], hi = stats[1], nlo = stats[2], nhi = stats[3], r = stats[4];
+  const float kx[3][3] = {{1.f, 0.f, -1.f}, {2.f, 0.f, -2.f}, {1.f, 0.f, -1.f}};
+  const float ky[3][3] = {{1.f, 2.f, 1.f}, {0.f, 0.f, 0.f}, {-1.f, -2.f, -1.f}};
+  float s0 = 0.f, s1 = 0.f;
+  for (int i = tid; i < n; i += 1024) {
+    const int b = i / HW, rem = i - b * HW;
+    const int py = rem / W, px = rem - py * W;
+    const float* g0 = g_sob + (int64_t)b * 2 * HW;
+    const float* g1 = g0 + HW;
+    float acc = 0.f;
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int yy = py - dy, xx = px - dx;
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W)
+          acc += kx[dy + 1][dx + 1] * __ldg(g0 + yy * W + xx) + ky[dy + 1][dx + 1] * __ldg(g1 + yy * W + xx);
+      }
+    const float g = g_y[i] + acc;
+    g_y[i] = g;
+    s0 += g;
+    s1 = fmaf(g, __ldg(x + i) - lo, s1);
+  }
+  const float S0 = cta1024_reduce(s0, [](float a, float b) { return a + b; }, redf);
+  const float S1 = cta1024_reduce(s1, [](float a, float b) { return a + b; }, redf);
+  const float a = inv_std / r;
+  const float cS1 = inv_std * S1 / (r * r);
+  const float t_lo = (cS1 - a * S0) / nlo, t_hi = -cS1 / nhi;
+  for (int i = tid; i < n; i += 1024) {  // every thread re-reads only what it wrote itself
+    const float v = __ldg(x + i);
+    float out = a * g_y[i];
+    if (v == lo) out += t_lo;
+    if (v == hi) out += t_hi;
+    grad[i] = out;
+  }
+}
+
+// carve-up of the caller's workspace (in floats)
+struct RegSimLayout {
+  int64_t stats, ones, y, sob, gstat, part_p, part_s, coef_p, coef_s, g_y, g_sob, total;
+  int tiles_p, tiles_s;
+};
+
+static RegSimLayout regsim_layout(int B, int H, int W, int p, int q) {
+  RegSimLayout L;
+  const int64_t HW = (int64_t)H * W;
+  auto tiles = [&](int k) { return ((H - k + 1 + NCC_T - 1) / NCC_T) * ((W - k + 1 + NCC_T - 1) / NCC_T); };
+  L.tiles_p = tiles(p);
+  L.tiles_s = tiles(q);
+  int64_t o = 0;
+  auto take = [&](int64_t n) { const int64_t at = o; o += (n + 3) & ~(int64_t)3; return at; };
+  L.stats = take(8);
+  L.ones = take(B);
+  L.y = take(B * HW);
+  L.sob = take(2 * B * HW);
+  L.gstat = take((int64_t)B * 6);
+  L.part_p = take((int64_t)B * L.tiles_p);
+  L.part_s = take((int64_t)B * 2 * L.tiles_s);
+  L.coef_p = take((int64_t)B * 4 * (H - p + 1) * (W - p + 1));
+  L.coef_s = take((int64_t)B * 2 * 4 * (H - q + 1) * (W - q + 1));
+  L.g_y = take(B * HW);
+  L.g_sob = take(2 * B * HW);
+  L.total = o;
+  return L;
+}
+
 }  // namespace xvr
 
 using namespace xvr;
@@ -368,4 +536,77 @@ extern "C" int xvr_sobel_bwd(const float* gout, int B, int H, int W, float* gx, 
   }
   sobel_bwd_kernel<<<dim3((W + 31) / 32, (H + 7) / 8, B), 256, 0, (cudaStream_t)stream>>>(gout, H, W, gx);
   return check_launch("xvr_sobel_bwd");
+}
+
+// ---- value and gradient of the registration similarity in nine launches (see regsim_prep_kernel).
+static bool regsim_args_ok(int B, int H, int W, int p, int q) {
+  return B > 0 && H > 0 && W > 0 && p >= 1 && q >= 1 && p <= H && p <= W && q <= H && q <= W && p <= 64 && q <= 64 &&
+         (int64_t)B * H * W <= ((int64_t)1 << 24);
+}
+
+extern "C" long long xvr_regsim_workspace_floats(int B, int H, int W, int patch_mncc, int patch_gncc) {
+  if (!regsim_args_ok(B, H, W, patch_mncc, patch_gncc)) return -1;
+  return regsim_layout(B, H, W, patch_mncc, patch_gncc).total;
+}
+
+// fixed (B,1,H,W): the transformed target X-ray; fixed_sobel (B,2,H,W) = Sobel(fixed); moving (B,1,H,W): raw DRRs.
+// score[0] = sum_b w_global NCC + w_patch NCC_p + w_grad NCC_q(Sobel) of (fixed, XrayTransforms(moving));
+// grad (B,1,H,W) = d score / d moving.  The transform is Standardize(std_eps) -> (. - mean) * inv_std.
+extern "C" int xvr_regsim(const float* fixed, const float* fixed_sobel, const float* moving, int B, int H, int W,
+                          float std_eps, float mean, float inv_std, int patch_mncc, int patch_gncc, float w_global,
+                          float w_patch, float w_grad, float ncc_eps, float* workspace, long long workspace_floats,
+                          float* score, float* grad, void* stream) {
+  if (!fixed || !fixed_sobel || !moving || !workspace || !score || !grad ||
+      !regsim_args_ok(B, H, W, patch_mncc, patch_gncc)) {
+    set_last_error("xvr_regsim: invalid argument (patches must be <= min(H, W, 64), B*H*W <= 2^24)");
+    return XVR_ERR_INVALID;
+  }
+  const int p = patch_mncc, q = patch_gncc;
+  const RegSimLayout L = regsim_layout(B, H, W, p, q);
+  if (workspace_floats < L.total) {
+    set_last_error("xvr_regsim: workspace smaller than xvr_regsim_workspace_floats()");
+    return XVR_ERR_INVALID;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  float* ws = workspace;
+  const int HW = H * W;
+  int rc;
+  regsim_prep_kernel<<<1, 1024, 0, st>>>(moving, B, H, W, std_eps, mean, inv_std, ws + L.stats, ws + L.ones, ws + L.y,
+                                         ws + L.sob);
+  if ((rc = check_launch("xvr_regsim/prep"))) return rc;
+
+  global_ncc_fwd_kernel<<<B, 1024, 0, st>>>(fixed, ws + L.y, HW, ncc_eps, ws + L.gstat);
+  if ((rc = check_launch("xvr_regsim/global"))) return rc;
+  const int nHp = H - p + 1, nWp = W - p + 1, nHq = H - q + 1, nWq = W - q + 1;
+  const size_t smem_fwd = ncc_smem(p > q ? p : q, 2), smem_bwd = ncc_smem(p > q ? p : q, 4);
+  if (smem_fwd > 48 * 1024)
+    cudaFuncSetAttribute(patch_ncc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fwd);
+  if (smem_bwd > 48 * 1024)
+    cudaFuncSetAttribute(patch_ncc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bwd);
+  patch_ncc_fwd_kernel<<<dim3((nWp + NCC_T - 1) / NCC_T, (nHp + NCC_T - 1) / NCC_T, B), dim3(NCC_T, NCC_T),
+                         ncc_smem(p, 2), st>>>(fixed, ws + L.y, H, W, p, ncc_eps, ws + L.part_p, ws + L.coef_p, nullptr);
+  if ((rc = check_launch("xvr_regsim/patch"))) return rc;
+  patch_ncc_fwd_kernel<<<dim3((nWq + NCC_T - 1) / NCC_T, (nHq + NCC_T - 1) / NCC_T, B * 2), dim3(NCC_T, NCC_T),
+                         ncc_smem(q, 2), st>>>(fixed_sobel, ws + L.sob, H, W, q, ncc_eps, ws + L.part_s, ws + L.coef_s,
+                                               nullptr);
+  if ((rc = check_launch("xvr_regsim/gradient patch"))) return rc;
+  regsim_score_kernel<<<1, 1024, 0, st>>>(ws + L.gstat, B, w_global, ws + L.part_p, B * L.tiles_p,
+                                          w_patch / ((float)nHp * nWp), ws + L.part_s, B * 2 * L.tiles_s,
+                                          w_grad / (2.f * nHq * nWq), score);
+  if ((rc = check_launch("xvr_regsim/score"))) return rc;
+
+  // d/dy of the three terms (gather form, see patch_ncc_bwd_kernel), then back through Sobel and the transform
+  global_ncc_bwd_kernel<<<dim3((HW + 255) / 256, B), 256, 0, st>>>(fixed, ws + L.y, ws + L.gstat, 2, ws + L.ones,
+                                                                   w_global / (float)HW, 1, HW, ws + L.g_y, 0);
+  if ((rc = check_launch("xvr_regsim/global bwd"))) return rc;
+  patch_ncc_bwd_kernel<<<dim3((W + NCC_T - 1) / NCC_T, (H + NCC_T - 1) / NCC_T, B), dim3(NCC_T, NCC_T), ncc_smem(p, 4),
+                         st>>>(fixed, ws + L.y, ws + L.coef_p, ws + L.ones, w_patch / ((float)nHp * nWp * p * p), 1, H,
+                               W, p, ws + L.g_y, 1);
+  if ((rc = check_launch("xvr_regsim/patch bwd"))) return rc;
+  patch_ncc_bwd_kernel<<<dim3((W + NCC_T - 1) / NCC_T, (H + NCC_T - 1) / NCC_T, B * 2), dim3(NCC_T, NCC_T),
+                         ncc_smem(q, 4), st>>>(fixed_sobel, ws + L.sob, ws + L.coef_s, ws + L.ones,
+                                               w_grad / (2.f * nHq * nWq * q * q), 2, H, W, q, ws + L.g_sob, 0);
+  if ((rc = check_launch("xvr_regsim/gradient patch bwd"))) return rc;
+  regsim_bwd_finish_kernel<<<1, 1024, 0, st>>>(moving, ws + L.g_sob, ws + L.stats, B, H, W, inv_std, ws + L.g_y, grad);
+  return check_launch("xvr_regsim/finish");
 }

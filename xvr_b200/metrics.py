@@ -10,10 +10,12 @@ PyTorch.
 import torch
 
 from . import _conventions as conv
+from . import _lib
 from ._lib import call, cuda_f32, ptr, stream
 from .pose import so3_log_map
 
 __all__ = [
+    "RegistrationSimilarity",
     "NormalizedCrossCorrelation2d",
     "MultiscaleNormalizedCrossCorrelation2d",
     "GradientNormalizedCrossCorrelation2d",
@@ -96,6 +98,59 @@ class _Sobel(torch.autograd.Function):
         if B > 0:
             call("xvr_sobel_bwd", ptr(gout), B, H, W, ptr(gx), stream())
         return gx
+
+
+class _RegSim(torch.autograd.Function):
+    """moving (B,1,H,W) raw DRRs -> scalar similarity to a fixed, transformed X-ray, value AND gradient in one C-ABI
+    call (nine launches, csrc/ncc.cu xvr_regsim); backward scales the saved gradient by the upstream scalar."""
+
+    @staticmethod
+    def forward(ctx, moving, fixed, fixed_sobel, cfg):
+        moving = cuda_f32(moving, "moving image")
+        if moving.shape != fixed.shape or moving.dim() != 4 or moving.shape[1] != 1:
+            raise ValueError(f"expected (B,1,H,W) images of equal shape; got {tuple(moving.shape)}, {tuple(fixed.shape)}")
+        B, _, H, W = moving.shape
+        score = torch.zeros((), device=moving.device, dtype=torch.float32)
+        grad = torch.zeros_like(moving)
+        if B > 0:
+            std_eps, mean, inv_std, p, q, w_global, w_patch, w_grad, eps = cfg
+            n = _lib.lib().xvr_regsim_workspace_floats(B, H, W, p, q)
+            if n < 0:
+                raise _lib.XvrB200Error(f"fused registration similarity does not support B={B}, {H}x{W}, patches {p}, {q}")
+            work = torch.empty(n, device=moving.device, dtype=torch.float32)
+            call("xvr_regsim", ptr(fixed), ptr(fixed_sobel), ptr(moving), B, H, W, std_eps, mean, inv_std, p, q,
+                 w_global, w_patch, w_grad, eps, ptr(work), n, ptr(score), ptr(grad), stream())
+        ctx.save_for_backward(grad)
+        return score
+
+    @staticmethod
+    def backward(ctx, gscore):
+        (grad,) = ctx.saved_tensors
+        return grad * gscore, None, None, None
+
+
+class RegistrationSimilarity(torch.nn.Module):
+    """The similarity one registration iteration maximises, from the RAW moving DRR to the scalar:
+
+        ``(beta * mNCC([None, p], [0.5, 0.5]) + (1 - beta) * GradNCC(q, sigma=0))(fixed, XrayTransforms(moving)).sum()``
+
+    (/root/reference/src/xvr/registrar/base.py:119-122, 245-252) as one fused value-and-gradient evaluation.
+    ``fixed`` is the already transformed target; its Sobel image is computed once here.  Covers the registration
+    defaults only: no ``Equalize``, no resize, no Gaussian blur in front of the Sobel operator."""
+
+    def __init__(self, fixed, mncc_patch_size=9, gncc_patch_size=11, beta=0.5, mean=0.15, std=0.1, std_eps=1e-6,
+                 eps=conv.NCC_EPS):
+        super().__init__()
+        fixed = cuda_f32(fixed.detach(), "fixed image")
+        self.register_buffer("fixed", fixed, persistent=False)
+        self.register_buffer("fixed_sobel", _Sobel.apply(fixed), persistent=False)
+        # x / std on a CUDA tensor multiplies by the fp32 reciprocal of the Python scalar (ATen div_true_kernel_cuda)
+        inv_std = float(torch.tensor(1.0, dtype=torch.float32) / torch.tensor(std, dtype=torch.float32))
+        self.cfg = (float(std_eps), float(mean), inv_std, int(mncc_patch_size), int(gncc_patch_size), 0.5 * beta,
+                    0.5 * beta, 1.0 - beta, float(eps))
+
+    def forward(self, moving):
+        return _RegSim.apply(moving, self.fixed, self.fixed_sobel, self.cfg)
 
 
 class NormalizedCrossCorrelation2d(torch.nn.Module):

@@ -18,7 +18,8 @@ import time
 import torch
 
 from ._lib import call, ptr, stream
-from .metrics import GradientNormalizedCrossCorrelation2d, MultiscaleNormalizedCrossCorrelation2d
+from .metrics import (GradientNormalizedCrossCorrelation2d, MultiscaleNormalizedCrossCorrelation2d,
+                      RegistrationSimilarity)
 from .pose import convert
 from .preprocess import XrayTransforms
 from .registration import Registration
@@ -118,7 +119,8 @@ class Registrar:
 
     def __init__(self, drr, scales="8", n_itrs="500", parameterization="euler_angles", convention="ZXY", lr_rot=1e-2,
                  lr_xyz=1e0, patience=10, threshold=1e-4, max_n_plateaus=3, crop=0, equalize=False, mncc_patch_size=9,
-                 gncc_patch_size=11, sigma=0.0, beta=0.5, use_cuda_graph=True, poll_every=16, fused_update=True):
+                 gncc_patch_size=11, sigma=0.0, beta=0.5, use_cuda_graph=True, poll_every=16, fused_update=True,
+                 fused_similarity=False):
         self.drr = drr
         self.scales = scales.split(",") if isinstance(scales, str) else [str(s) for s in scales]
         self.n_itrs = [int(n) for n in n_itrs.split(",")] if isinstance(n_itrs, str) else [int(n) for n in n_itrs]
@@ -129,6 +131,10 @@ class Registrar:
         self.patience, self.threshold, self.max_n_plateaus = patience, threshold, max_n_plateaus
         self.crop, self.equalize = crop, equalize
         self.beta = beta
+        self.patches, self.sigma = (mncc_patch_size, gncc_patch_size), sigma
+        # XrayTransforms + similarity + their backward as nine launches instead of ~60 (csrc/ncc.cu, xvr_regsim).
+        # Opt-in until it has been timed on a B200; only for the defaults it covers (no Equalize, sigma = 0).
+        self.fused_similarity = bool(fused_similarity) and not equalize and sigma == 0.0
         self.sim1 = MultiscaleNormalizedCrossCorrelation2d([None, mncc_patch_size], [0.5, 0.5])
         self.sim2 = GradientNormalizedCrossCorrelation2d(gncc_patch_size, sigma)
         self.use_cuda_graph = use_cuda_graph
@@ -139,13 +145,23 @@ class Registrar:
     def imagesim(self, x, y):
         return self.beta * self.sim1(x, y) + (1 - self.beta) * self.sim2(x, y)
 
+    def _score(self, transform, img, raw):
+        """Scalar similarity of the raw DRR batch ``raw`` to the transformed target ``img`` (summed over the batch)."""
+        if self.fused_similarity:
+            if getattr(self, "_fsim_for", None) is not img:  # one fixed image (and its Sobel) per stage
+                self._fsim = RegistrationSimilarity(img, *self.patches, beta=self.beta, mean=transform.mean,
+                                                    std=transform.std, std_eps=transform.standardize.eps,
+                                                    eps=self.sim1.eps)
+                self._fsim_for = img
+            return self._fsim(raw)
+        return self.imagesim(img, transform(raw)).sum()
+
     # ------------------------------------------------------------------ one iteration (device only)
     def _iteration(self, reg, transform, img, state, sched, log):
         """forward -> similarity -> backward -> Adam(maximize) -> plateau logic -> trajectory row; no host sync."""
         reg.rotation.grad = None
         reg.translation.grad = None
-        pred = transform(reg())
-        loss = self.imagesim(img, pred).sum()
+        loss = self._score(transform, img, reg())
         loss.backward()
         if self.fused_update:
             hyper = (ctypes.c_double * 9)(0.9, 0.999, 1e-8, sched.factor, sched.patience, sched.threshold, sched.min_lr,
@@ -232,7 +248,7 @@ class Registrar:
                 print(f"stage {stage}: {count} iterations, similarity {last:.4f}")
 
         with torch.no_grad():
-            final = float(self.imagesim(img, transform(reg())).sum())
+            final = float(self._score(transform, img, reg()))
             pose = reg.pose
         rows = torch.cat(stage_rows) if stage_rows else torch.zeros(0, 1 + n_rot + 5)
         traj = convert(rows[:, 1:1 + n_rot], rows[:, 1 + n_rot:4 + n_rot], parameterization=self.parameterization,
