@@ -337,7 +337,8 @@ def main():
         total = world * B * args.steps
         value = total / (ms * 1e-3)
         peak, peak_src = peaks()
-        name = "xvr_trilinear_drr_fwd" if "xvr_trilinear_drr_fwd" in kernel_ms else "xvr_trilinear_rays_fwd"
+        name = next((k for k in ("xvr_trilinear_drr_fwd", "xvr_trilinear_drr_fwd_staged") if k in kernel_ms),
+                    "xvr_trilinear_rays_fwd")
         k_ms = kernel_ms.get(name, [])
         k_avg = sum(k_ms) / len(k_ms) if k_ms else float("nan")
         alg = B * algorithmic_bytes_fwd(H, W, N_POINTS)
@@ -354,6 +355,7 @@ def main():
             "roofline": {"bound": "hbm", "kernel": "trilinear_fwd_kernel<JAC=true> (one gather pass yields the DRR "
                          "and its per-ray pose Jacobian; the backward is a 28 B/ray epilogue)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "entry_point": name,
                          "traffic": measured_traffic(name, B) if (H, W, args.vol) == (DET, DET, VOL_N) else None,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": alg,
                          "kernel_ms": k_avg},

@@ -117,6 +117,28 @@ __device__ __forceinline__ float linspace01(int k, int n, float step) {
   return (k < n / 2) ? step * (float)k : 1.0f - step * (float)(n - 1 - k);
 }
 
+// Trilinear blend of the 8 corner values c[x][y][z] at fractional offsets (fx, fy, fz): along z (contiguous), then
+// y, then x.  GRAD also returns dV/dx.  Shared by every gather path (texture, global loads, staged bricks) so that
+// they produce bit-identical samples.
+template <bool GRAD>
+__device__ __forceinline__ float trilinear_interp(float c000, float c001, float c010, float c011, float c100,
+                                                  float c101, float c110, float c111, float fx, float fy, float fz,
+                                                  float g[3]) {
+  float dz00 = c001 - c000, dz01 = c011 - c010, dz10 = c101 - c100, dz11 = c111 - c110;
+  float c00 = fmaf(fz, dz00, c000), c01 = fmaf(fz, dz01, c010);
+  float c10 = fmaf(fz, dz10, c100), c11 = fmaf(fz, dz11, c110);
+  float dy0 = c01 - c00, dy1 = c11 - c10;
+  float c0 = fmaf(fy, dy0, c00), c1 = fmaf(fy, dy1, c10);
+  float dx = c1 - c0;
+  if (GRAD) {
+    g[0] = dx;
+    g[1] = fmaf(fx, dy1 - dy0, dy0);
+    float gz0 = fmaf(fy, dz01 - dz00, dz00), gz1 = fmaf(fy, dz11 - dz10, dz10);
+    g[2] = fmaf(fx, gz1 - gz0, gz0);
+  }
+  return fmaf(fx, dx, c0);
+}
+
 // One trilinear sample with zero padding (grid_sample mode="bilinear", padding_mode="zeros",
 // align_corners=True on a grid normalised with dims = shape-1, i.e. the sampler coordinate IS the voxel index;
 // ATen/native/cuda/GridSampler.cuh:23-31 and the out-of-bounds handling at :225-227).
@@ -168,20 +190,7 @@ __device__ __forceinline__ float sample_trilinear(const Vol& v, float x, float y
     c110 = (x1 && y1 && z0) ? __ldg(p + v.s0 + v.s1) : 0.f;
     c111 = (x1 && y1 && z1) ? __ldg(p + v.s0 + v.s1 + 1) : 0.f;
   }
-  // interpolate along z (contiguous), then y, then x
-  float dz00 = c001 - c000, dz01 = c011 - c010, dz10 = c101 - c100, dz11 = c111 - c110;
-  float c00 = fmaf(fz, dz00, c000), c01 = fmaf(fz, dz01, c010);
-  float c10 = fmaf(fz, dz10, c100), c11 = fmaf(fz, dz11, c110);
-  float dy0 = c01 - c00, dy1 = c11 - c10;
-  float c0 = fmaf(fy, dy0, c00), c1 = fmaf(fy, dy1, c10);
-  float dx = c1 - c0;
-  if (GRAD) {
-    g[0] = dx;
-    g[1] = fmaf(fx, dy1 - dy0, dy0);
-    float gz0 = fmaf(fy, dz01 - dz00, dz00), gz1 = fmaf(fy, dz11 - dz10, dz10);
-    g[2] = fmaf(fx, gz1 - gz0, gz0);
-  }
-  return fmaf(fx, dx, c0);
+  return trilinear_interp<GRAD>(c000, c001, c010, c011, c100, c101, c110, c111, fx, fy, fz, g);
 }
 
 // Nearest label lookup at the same sampler coordinate (grid_sample mode="nearest", align_corners=True,

@@ -181,6 +181,11 @@ class _RenderRays(torch.autograd.Function):
         return None, gsource, gtarget, graylen, None, None, None, None, None, None
 
 
+# Diagnostics of the staged variant: set _staged_stats["tensor"] to a zeroed int64 CUDA tensor of 3 elements to collect
+# {samples served from shared memory, from global memory, barrier time-outs}.
+_staged_stats = {}
+
+
 class _RenderDRR(torch.autograd.Function):
     """Fused DRR: rays are generated inside the kernel from cam2vox (B,3,4) and the detector basis, so no
     (B,N,3) tensor exists; the backward reduces the saved per-ray Jacobian straight to dL/dcam2vox (B,3,4) and,
@@ -199,8 +204,13 @@ class _RenderDRR(torch.autograd.Function):
         if B == 0:  # an empty pose batch renders to an empty image batch; nothing to launch
             ctx.save_for_backward(jac)
             return out
-        call("xvr_trilinear_drr_fwd", ptr(volume), voltex, *volume.shape, ptr(cam2vox), ptr(cam2world), det, B, H, W,
-             *args, lw, cw, ptr(out), ptr(jac), stream())
+        if os.environ.get("XVR_B200_STAGED", "0") == "1":
+            # opt-in, not yet run on a GPU: bricks staged in shared memory by TMA bulk copies (csrc/trilinear_staged.cu)
+            call("xvr_trilinear_drr_fwd_staged", ptr(volume), *volume.shape, ptr(cam2vox), ptr(cam2world), det, B, H, W,
+                 *args, ptr(out), ptr(jac), ptr(_staged_stats.get("tensor")), stream())
+        else:
+            call("xvr_trilinear_drr_fwd", ptr(volume), voltex, *volume.shape, ptr(cam2vox), ptr(cam2world), det, B, H,
+                 W, *args, lw, cw, ptr(out), ptr(jac), stream())
         ctx.det = (det, B, H, W, args, tuple(volume.shape))
         ctx.save_for_backward(jac, *((cam2vox, cam2world) if ctx.needs_input_grad[0] else ()))
         return out
