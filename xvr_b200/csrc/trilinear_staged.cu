@@ -268,6 +268,9 @@ __global__ void __launch_bounds__(256, 3) trilinear_fwd_staged_kernel(const Stag
     // ---- 2. stage the box: one bulk copy per row that intersects the volume, zeros elsewhere
     if (desc.staged != 0) {  // CTA-uniform: every thread arrives at the barrier exactly once per staged slab
       if (!broken) {
+        // the buffer was read (and its padding written) through the generic proxy; the bulk copies below write it
+        // through the async proxy
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         const int rows = E0 * E1;
         const int c_lo = max(bl2, 0), c_hi = min(bl2 + E2, size[2]);  // multiples of 4
         uint32_t bytes = 0;
