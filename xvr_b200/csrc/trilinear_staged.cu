@@ -25,9 +25,19 @@
 
 namespace xvr {
 
-constexpr int ST_T = 16;        // detector tile edge per CTA
-constexpr int ST_K = 4;         // voxel layers per slab
-constexpr int ST_CAP = 12288;   // floats in the staging buffer (48 KB -> three to four CTAs per SM)
+// Tuning knobs (override with XVR_B200_NVCC_FLAGS="-DXVR_ST_K=8 -DXVR_ST_CAP=24576 -DXVR_ST_MIN_CTAS=2")
+#ifndef XVR_ST_K
+#define XVR_ST_K 4
+#endif
+#ifndef XVR_ST_CAP
+#define XVR_ST_CAP 12288
+#endif
+#ifndef XVR_ST_MIN_CTAS
+#define XVR_ST_MIN_CTAS 3
+#endif
+constexpr int ST_T = 16;             // detector tile edge per CTA
+constexpr int ST_K = XVR_ST_K;       // voxel layers per slab
+constexpr int ST_CAP = XVR_ST_CAP;   // floats in the staging buffer (48 KB -> three to four CTAs per SM)
 
 struct StagedParams {
   Vol vol;
@@ -92,7 +102,7 @@ __device__ __forceinline__ float pick3(const float v[3], int a) { return a == 0 
 __device__ __forceinline__ int slab_of(int cell) { return (max(cell, -ST_K) + ST_K) / ST_K; }
 
 template <bool JAC>
-__global__ void __launch_bounds__(256, 3) trilinear_fwd_staged_kernel(const StagedParams p) {
+__global__ void __launch_bounds__(256, XVR_ST_MIN_CTAS) trilinear_fwd_staged_kernel(const StagedParams p) {
   extern __shared__ __align__(16) float box[];  // ST_CAP floats
   __shared__ __align__(8) unsigned long long mbar_storage;
   __shared__ BoxDesc descs[2];  // double-buffered: warp 0 publishes slab t+1 while slower warps still read slab t
