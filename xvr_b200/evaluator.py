@@ -22,22 +22,24 @@ class Evaluator:
     """
 
     def __init__(self, drr, fiducials):
-        self.drr = drr
-        self.fiducials = fiducials
-        self.geodesic = DoubleGeodesicSE3(drr.detector.sdd, eps=0.0)
+        self.drr, self.fiducials = drr, fiducials
+        # eps = 0: identical poses must score exactly zero (the loss keeps an eps for its square root's gradient)
+        self._pose_distance = DoubleGeodesicSE3(drr.detector.sdd, eps=0.0)
+
+    @staticmethod
+    def _mean_distance(a, b):
+        """Mean Euclidean distance between corresponding points, (B, n, d) x (B, n, d) -> (B,)."""
+        return torch.linalg.vector_norm(a - b, dim=-1).mean(dim=-1)
 
     def __call__(self, true_pose, pred_pose):
-        x = self.drr.perspective_projection(pred_pose, self.fiducials)
-        y = self.drr.perspective_projection(true_pose, self.fiducials)
-        mpe = (self.drr.detector.delx * (x - y)).norm(dim=-1).mean(dim=-1)
-
-        x = self.drr.inverse_projection(pred_pose, x)
-        y = self.drr.inverse_projection(true_pose, y)
-        mrpe = (x - y).norm(dim=-1).mean(dim=-1)
-
-        x = pred_pose(self.fiducials)
-        y = true_pose(self.fiducials)
-        mtre = (x - y).norm(dim=-1).mean(dim=-1)
-
-        *_, dgeo = self.geodesic(true_pose, pred_pose)
-        return torch.stack([mpe, mrpe, mtre, dgeo], dim=-1).squeeze().cpu().tolist()
+        poses = {"true": true_pose, "pred": pred_pose}
+        on_detector = {k: self.drr.perspective_projection(p, self.fiducials) for k, p in poses.items()}
+        lifted = {k: self.drr.inverse_projection(p, on_detector[k]) for k, p in poses.items()}
+        moved = {k: p(self.fiducials) for k, p in poses.items()}
+        errors = [
+            self.drr.detector.delx * self._mean_distance(on_detector["pred"], on_detector["true"]),  # mPE
+            self._mean_distance(lifted["pred"], lifted["true"]),                                     # mRPE
+            self._mean_distance(moved["pred"], moved["true"]),                                       # mTRE
+            self._pose_distance(true_pose, pred_pose)[2],                                            # dGeo
+        ]
+        return torch.stack(errors, dim=-1).squeeze().cpu().tolist()
