@@ -81,12 +81,13 @@ int xvr_trilinear_drr_bwd_volume(const float* cam2vox, const float* vox2cam, con
                                  int accumulate, void* stream);
 /* Opt-in variant of xvr_trilinear_drr_fwd (NOT yet run on a GPU, csrc/trilinear_staged.cu): 16x16 detector tiles
  * march the volume slab by slab, each slab's brick staged in shared memory by cp.async.bulk (TMA) behind an mbarrier;
- * same arithmetic and summation order, so out / jac are bit-identical to xvr_trilinear_drr_fwd.  stats: NULL or a
- * zeroed DEVICE unsigned long long[3] = {samples served from shared memory, from global memory, barrier time-outs}. */
+ * same arithmetic and summation order, so out / jac are bit-identical to xvr_trilinear_drr_fwd.  stages: 1 = one
+ * staging buffer, 2 = double-buffered (copies of slab t+1 overlap the march of slab t).  stats: NULL or a zeroed
+ * DEVICE unsigned long long[3] = {samples served from shared memory, from global memory, barrier time-outs}. */
 int xvr_trilinear_drr_fwd_staged(const float* volume, int D0, int D1, int D2, const float* cam2vox,
                                  const float* cam2world, const float* det9, int B, int det_h, int det_w, int n_points,
-                                 int step_mode, float eps, float* out, float* jac, unsigned long long* stats,
-                                 void* stream);
+                                 int step_mode, float eps, int stages, float* out, float* jac,
+                                 unsigned long long* stats, void* stream);
 /* formulation of the volume gradient: 2 = brick-local scatter in shared memory (default), 1 = voxel-centric gather
  * (independent cross-check); both atomics-free and deterministic, same result (csrc/volgrad.cu) */
 int xvr_set_volgrad_version(int version);

@@ -101,14 +101,15 @@ _STAGED = pytest.mark.skipif(os.environ.get("XVR_B200_RUN_UNVALIDATED") != "1",
                              reason="staged-brick kernel: never run on a GPU; set XVR_B200_RUN_UNVALIDATED=1")
 
 
-def _both_kernels(drr, rot, xyz, monkeypatch):
+def _both_kernels(drr, rot, xyz, monkeypatch, stages="1"):
+    """(texture kernel, staged kernel with `stages` buffers): image, pose gradients, staging statistics."""
     from xvr_b200 import renderers
 
     outs = []
-    for staged in ("0", "1"):
+    for staged in ("0", stages):
         monkeypatch.setenv("XVR_B200_STAGED", staged)
         stats = torch.zeros(3, dtype=torch.int64, device=rot.device)
-        renderers._staged_stats["tensor"] = stats if staged == "1" else None
+        renderers._staged_stats["tensor"] = stats if staged != "0" else None
         r, x = rot.clone().requires_grad_(), xyz.clone().requires_grad_()
         img = drr(xvr_b200.convert(r, x, parameterization="euler_angles", convention="ZXY"))
         wimg = torch.rand(img.shape, generator=torch.Generator().manual_seed(4)).to(img.device)
@@ -119,13 +120,14 @@ def _both_kernels(drr, rot, xyz, monkeypatch):
 
 
 @_STAGED
+@pytest.mark.parametrize("stages", ["1", "2"])
 @pytest.mark.parametrize("n,h", [(64, 32), (96, 48), (128, 80)])
-def test_staged_bricks_render_bit_identical_images_and_gradients(cuda, monkeypatch, n, h):
+def test_staged_bricks_render_bit_identical_images_and_gradients(cuda, monkeypatch, n, h, stages):
     from tests._scene import make_drr, pose_params
 
     drr = make_drr(n, h)
     rot, xyz = pose_params(3, seed=31)
-    (img0, gr0, gx0, _), (img1, gr1, gx1, stats) = _both_kernels(drr, rot, xyz, monkeypatch)
+    (img0, gr0, gx0, _), (img1, gr1, gx1, stats) = _both_kernels(drr, rot, xyz, monkeypatch, stages)
     assert torch.equal(img1, img0) and torch.equal(gr1, gr0) and torch.equal(gx1, gx0)
     shared, glob, timeouts = stats
     assert timeouts == 0
@@ -133,7 +135,8 @@ def test_staged_bricks_render_bit_identical_images_and_gradients(cuda, monkeypat
 
 
 @_STAGED
-def test_staged_bricks_edge_poses_and_partial_tiles(cuda, monkeypatch):
+@pytest.mark.parametrize("stages", ["1", "2"])
+def test_staged_bricks_edge_poses_and_partial_tiles(cuda, monkeypatch, stages):
     """Non-square detector that is not a multiple of the 16 x 16 tile, anisotropic voxels, a volume whose rows are
     not 16-byte multiples (global-memory service), rays missing / grazing the volume, a source inside it."""
     import numpy as np
@@ -143,7 +146,8 @@ def test_staged_bricks_edge_poses_and_partial_tiles(cuda, monkeypatch):
     from xvr_b200.data import read
 
     drr = make_drr(64, 32)
-    a, b = _both_kernels(drr, torch.tensor(EDGE_ROT, device=cuda), torch.tensor(EDGE_XYZ, device=cuda), monkeypatch)
+    a, b = _both_kernels(drr, torch.tensor(EDGE_ROT, device=cuda), torch.tensor(EDGE_XYZ, device=cuda), monkeypatch,
+                         stages)
     assert all(torch.equal(u, v) for u, v in zip(a[:3], b[:3])) and b[3][2] == 0
 
     from tests._scene import pose_params
@@ -153,7 +157,7 @@ def test_staged_bricks_edge_poses_and_partial_tiles(cuda, monkeypatch):
         drr = xvr_b200.DRR(read(vol, affine=np.diag([2.0, 1.5, 2.5, 1.0])), 1020.0, 24, 6.0, width=40, dely=5.0,
                            x0=7.0, y0=-11.0, renderer="trilinear", reverse_x_axis=True).to(cuda)
         rot, xyz = pose_params(3, seed=5)
-        a, b = _both_kernels(drr, rot, xyz, monkeypatch)
+        a, b = _both_kernels(drr, rot, xyz, monkeypatch, stages)
         assert all(torch.equal(u, v) for u, v in zip(a[:3], b[:3])) and b[3][2] == 0
         if shape[2] % 4:
             assert b[3][0] == 0  # rows of 50 floats cannot be bulk-copied: everything comes from global memory

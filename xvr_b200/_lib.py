@@ -31,8 +31,8 @@ _SIGNATURES = {
         [P, P, c_int, c_int, c_int, P, P, ctypes.POINTER(c_float), c_int, c_int, c_int, c_int, c_int, c_float, c_int,
          c_int, P, P, P], c_int),
     "xvr_trilinear_drr_fwd_staged": (
-        [P, c_int, c_int, c_int, P, P, ctypes.POINTER(c_float), c_int, c_int, c_int, c_int, c_int, c_float, P, P, P, P],
-        c_int),
+        [P, c_int, c_int, c_int, P, P, ctypes.POINTER(c_float), c_int, c_int, c_int, c_int, c_int, c_float, c_int, P, P,
+         P, P], c_int),
     "xvr_drr_jac_bwd": ([P, P, ctypes.POINTER(c_float), c_int, c_int, c_int, P, P, P], c_int),
     "xvr_drr_jac_bwd_slices": ([c_int, c_int], c_int),
     "xvr_trilinear_drr_bwd_volume": (

@@ -101,11 +101,11 @@ __device__ __forceinline__ float pick3(const float v[3], int a) { return a == 0 
 // slab number of a cell index (cells -ST_K .. -1 -> 0, 0 .. ST_K-1 -> 1, ...); first cell of slab n is (n-1)*ST_K
 __device__ __forceinline__ int slab_of(int cell) { return (max(cell, -ST_K) + ST_K) / ST_K; }
 
-template <bool JAC>
-__global__ void __launch_bounds__(256, XVR_ST_MIN_CTAS) trilinear_fwd_staged_kernel(const StagedParams p) {
-  extern __shared__ __align__(16) float box[];  // ST_CAP floats
-  __shared__ __align__(8) unsigned long long mbar_storage;
-  __shared__ BoxDesc descs[2];  // double-buffered: warp 0 publishes slab t+1 while slower warps still read slab t
+template <bool JAC, int STAGES>
+__global__ void __launch_bounds__(256, STAGES == 1 ? XVR_ST_MIN_CTAS : 2) trilinear_fwd_staged_kernel(const StagedParams p) {
+  extern __shared__ __align__(16) float box[];  // STAGES * ST_CAP floats
+  __shared__ __align__(8) unsigned long long mbar_storage[2];
+  __shared__ BoxDesc descs[3];
   __shared__ int t_first, t_last;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -120,10 +120,11 @@ __global__ void __launch_bounds__(256, XVR_ST_MIN_CTAS) trilinear_fwd_staged_ker
   const int n = inside ? pi * p.W + pj : 0;
   const int np = p.n_points;
   const int size[3] = {p.vol.D0, p.vol.D1, p.vol.D2};
-  const uint32_t bar = smem_u32(&mbar_storage);
+  const uint32_t bar = smem_u32(&mbar_storage[0]);  // the second barrier sits 8 bytes further
 
   if (tid == 0) {
     mbar_init(bar, 256);
+    mbar_init(bar + 8u, 256);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     t_first = INT_MAX;
     t_last = INT_MIN;
@@ -217,139 +218,181 @@ __global__ void __launch_bounds__(256, XVR_ST_MIN_CTAS) trilinear_fwd_staged_ker
   bool have = false;
   float cu = 0.f, cx = 0.f, cy = 0.f, cz = 0.f;
   int ct = 0;
-  uint32_t phase = 0;
-  bool broken = false;  // a barrier wait timed out: this thread stops trusting the staging buffer
+  bool broken = false;  // a barrier wait timed out: this thread stops trusting the staging buffers
 
-  for (int t = tf; t <= tl; ++t) {
+  // ---- 1. box of slab t (warp 0; lanes 0-3: corner rays at plane loA, lanes 4-7: at plane loA + ST_K)
+  auto publish_box = [&](int t, BoxDesc& desc) {
     const int slab = forward ? t : -t;
     const int loA = (slab - 1) * ST_K;
-    BoxDesc& desc = descs[(t - tf) & 1];
-    // ---- 1. box of this slab (warp 0; lanes 0-3: corner rays at plane loA, lanes 4-7: at plane loA + ST_K)
-    if (warp == 0) {
-      float v1 = 0.f, v2 = 0.f;
-      bool ok = true;
-      if (lane < 8) {
-        const float plane = (float)(loA + ((lane & 4) ? ST_K : 0));
-        ok = fabsf(qdA) > 1e-12f;
-        const float al = ok ? (plane - qsA) / qdA : 0.f;
-        v1 = fmaf(al, qd1, qs1);
-        v2 = fmaf(al, qd2, qs2);
-        ok = ok && fabsf(v1) < 1e8f && fabsf(v2) < 1e8f;
-      }
-      float mn1 = lane < 8 ? v1 : INFINITY, mx1 = lane < 8 ? v1 : -INFINITY;
-      float mn2 = lane < 8 ? v2 : INFINITY, mx2 = lane < 8 ? v2 : -INFINITY;
-      unsigned bad = __ballot_sync(0xffffffffu, !ok);
-#pragma unroll
-      for (int o = 4; o > 0; o >>= 1) {
-        mn1 = fminf(mn1, __shfl_xor_sync(0xffffffffu, mn1, o));
-        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, o));
-        mn2 = fminf(mn2, __shfl_xor_sync(0xffffffffu, mn2, o));
-        mx2 = fmaxf(mx2, __shfl_xor_sync(0xffffffffu, mx2, o));
-      }
-      if (lane == 0) {
-        // cells loA .. loA+K-1 need layers loA .. loA+K; on the other axes one cell of margin each side (the
-        // per-sample positions are rounded differently from this bound) plus the upper corner
-        const int l1 = (int)floorf(mn1) - 1, h1 = (int)floorf(mx1) + 2;
-        const int l2 = (int)floorf(mn2) - 1, h2 = (int)floorf(mx2) + 2;
-        int lo[3], hi[3];
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {  // nothing beyond one layer of zero padding is ever read
-          lo[a] = max(a == A ? loA : (a == O1 ? l1 : l2), -1);
-          hi[a] = min(a == A ? loA + ST_K : (a == O1 ? h1 : h2), size[a]);
-        }
-        lo[2] &= ~3;                       // 16-byte rows (two's complement: -1 -> -4)
-        hi[2] = ((hi[2] + 4) & ~3) - 1;
-        long long elems = 1;
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-          desc.lo[a] = lo[a];
-          desc.E[a] = hi[a] - lo[a] + 1;
-          elems *= (long long)max(desc.E[a], 0);
-        }
-        desc.staged = bad == 0 && elems > 0 && elems <= ST_CAP && (size[2] & 3) == 0 &&
-                      ((size_t)p.vol.data & 15) == 0;
-      }
+    float v1 = 0.f, v2 = 0.f;
+    bool ok = true;
+    if (lane < 8) {
+      const float plane = (float)(loA + ((lane & 4) ? ST_K : 0));
+      ok = fabsf(qdA) > 1e-12f;
+      const float al = ok ? (plane - qsA) / qdA : 0.f;
+      v1 = fmaf(al, qd1, qs1);
+      v2 = fmaf(al, qd2, qs2);
+      ok = ok && fabsf(v1) < 1e8f && fabsf(v2) < 1e8f;
     }
-    __syncthreads();  // everyone is done with the previous slab's buffer; the new box is published
+    float mn1 = lane < 8 ? v1 : INFINITY, mx1 = lane < 8 ? v1 : -INFINITY;
+    float mn2 = lane < 8 ? v2 : INFINITY, mx2 = lane < 8 ? v2 : -INFINITY;
+    const unsigned bad = __ballot_sync(0xffffffffu, !ok);
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+      mn1 = fminf(mn1, __shfl_xor_sync(0xffffffffu, mn1, o));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, o));
+      mn2 = fminf(mn2, __shfl_xor_sync(0xffffffffu, mn2, o));
+      mx2 = fmaxf(mx2, __shfl_xor_sync(0xffffffffu, mx2, o));
+    }
+    if (lane == 0) {
+      // cells loA .. loA+K-1 need layers loA .. loA+K; on the other axes one cell of margin each side (the
+      // per-sample positions are rounded differently from this bound) plus the upper corner
+      const int l1 = (int)floorf(mn1) - 1, h1 = (int)floorf(mx1) + 2;
+      const int l2 = (int)floorf(mn2) - 1, h2 = (int)floorf(mx2) + 2;
+      int lo[3], hi[3];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {  // nothing beyond one layer of zero padding is ever read
+        lo[a] = max(a == A ? loA : (a == O1 ? l1 : l2), -1);
+        hi[a] = min(a == A ? loA + ST_K : (a == O1 ? h1 : h2), size[a]);
+      }
+      lo[2] &= ~3;  // 16-byte rows (two's complement: -1 -> -4)
+      hi[2] = ((hi[2] + 4) & ~3) - 1;
+      long long elems = 1;
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        desc.lo[a] = lo[a];
+        desc.E[a] = hi[a] - lo[a] + 1;
+        elems *= (long long)max(desc.E[a], 0);
+      }
+      desc.staged = bad == 0 && elems > 0 && elems <= ST_CAP && (size[2] & 3) == 0 && ((size_t)p.vol.data & 15) == 0;
+    }
+  };
+
+  // ---- 2. stage a box: one bulk copy per row that intersects the volume, zeros elsewhere.  Called by every thread
+  // (CTA-uniform on desc.staged): every thread arrives at `bar_addr` exactly once per staged box.
+  auto stage_box = [&](const BoxDesc& desc, float* buf, uint32_t bar_addr) {
+    if (desc.staged == 0) return;
+    if (broken) {
+      mbar_arrive(bar_addr);
+      return;
+    }
+    // the buffer was read (and its padding written) through the generic proxy; the bulk copies write it through the
+    // async proxy
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     const int bl0 = desc.lo[0], bl1 = desc.lo[1], bl2 = desc.lo[2];
     const int E0 = desc.E[0], E1 = desc.E[1], E2 = desc.E[2];
-    bool staged = desc.staged != 0 && !broken;
-
-    // ---- 2. stage the box: one bulk copy per row that intersects the volume, zeros elsewhere
-    if (desc.staged != 0) {  // CTA-uniform: every thread arrives at the barrier exactly once per staged slab
-      if (!broken) {
-        // the buffer was read (and its padding written) through the generic proxy; the bulk copies below write it
-        // through the async proxy
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        const int rows = E0 * E1;
-        const int c_lo = max(bl2, 0), c_hi = min(bl2 + E2, size[2]);  // multiples of 4
-        uint32_t bytes = 0;
-        for (int r = tid; r < rows; r += 256) {
-          const int g0 = bl0 + r / E1, g1 = bl1 + r % E1;
-          if ((unsigned)g0 < (unsigned)size[0] && (unsigned)g1 < (unsigned)size[1] && c_hi > c_lo)
-            bytes += (uint32_t)(c_hi - c_lo) * 4u;
-        }
-        if (bytes) mbar_arrive_expect_tx(bar, bytes); else mbar_arrive(bar);
-        for (int r = tid; r < rows; r += 256) {
-          const int g0 = bl0 + r / E1, g1 = bl1 + r % E1;
-          float* row = box + (size_t)r * E2;
-          const bool in = (unsigned)g0 < (unsigned)size[0] && (unsigned)g1 < (unsigned)size[1] && c_hi > c_lo;
-          const int z_lo = in ? c_lo - bl2 : E2, z_hi = in ? c_hi - bl2 : E2;  // [z_lo, z_hi) comes from the volume
-          for (int c = 0; c < z_lo; ++c) row[c] = 0.f;
-          for (int c = z_hi; c < E2; ++c) row[c] = 0.f;
-          if (in)
-            bulk_g2s(smem_u32(row + z_lo), p.vol.data + ((int64_t)g0 * p.vol.s0 + (int64_t)g1 * p.vol.s1 + c_lo),
-                     (uint32_t)(c_hi - c_lo) * 4u, bar);
-        }
-      } else {
-        mbar_arrive(bar);
-      }
-      __syncthreads();  // the zero fills are visible
-      if (!broken) {
-        bool done = false;
-        for (int spin = 0; spin < (1 << 16) && !done; ++spin) done = mbar_try_wait(bar, phase & 1u);
-        if (!done) {
-          broken = true;
-          staged = false;
-          ++n_timeout;
-        }
-      }
-      ++phase;
+    const int rows = E0 * E1;
+    const int c_lo = max(bl2, 0), c_hi = min(bl2 + E2, size[2]);  // multiples of 4
+    uint32_t bytes = 0;
+    for (int r = tid; r < rows; r += 256) {
+      const int g0 = bl0 + r / E1, g1 = bl1 + r % E1;
+      if ((unsigned)g0 < (unsigned)size[0] && (unsigned)g1 < (unsigned)size[1] && c_hi > c_lo)
+        bytes += (uint32_t)(c_hi - c_lo) * 4u;
     }
+    if (bytes) mbar_arrive_expect_tx(bar_addr, bytes); else mbar_arrive(bar_addr);
+    for (int r = tid; r < rows; r += 256) {
+      const int g0 = bl0 + r / E1, g1 = bl1 + r % E1;
+      float* row = buf + (size_t)r * E2;
+      const bool in = (unsigned)g0 < (unsigned)size[0] && (unsigned)g1 < (unsigned)size[1] && c_hi > c_lo;
+      const int z_lo = in ? c_lo - bl2 : E2, z_hi = in ? c_hi - bl2 : E2;  // [z_lo, z_hi) comes from the volume
+      for (int c = 0; c < z_lo; ++c) row[c] = 0.f;
+      for (int c = z_hi; c < E2; ++c) row[c] = 0.f;
+      if (in)
+        bulk_g2s(smem_u32(row + z_lo), p.vol.data + ((int64_t)g0 * p.vol.s0 + (int64_t)g1 * p.vol.s1 + c_lo),
+                 (uint32_t)(c_hi - c_lo) * 4u, bar_addr);
+    }
+  };
 
-    // ---- 3. this ray's samples whose cell lies in the slab
-    if (regular) {
-      while (k < np) {
-        if (!have) {
-          cu = linspace01(k, np, lstep);
-          const float alpha = fmaf(cu, span, ar.amin);
-          cx = fmaf(alpha, d[0], s[0]);
-          cy = fmaf(alpha, d[1], s[1]);
-          cz = fmaf(alpha, d[2], s[2]);
-          const float pa = A == 0 ? cx : (A == 1 ? cy : cz);
-          const int cs = slab_of((int)floorf(pa));
-          ct = forward ? cs : -cs;
-          have = true;
-        }
-        if (ct > t) break;  // belongs to a later slab
-        float g[3], v;
-        const float fx0 = floorf(cx), fy0 = floorf(cy), fz0 = floorf(cz);
-        const int lx = (int)fx0 - bl0, ly = (int)fy0 - bl1, lz = (int)fz0 - bl2;
-        if (staged && ct == t && (unsigned)lx < (unsigned)(E0 - 1) && (unsigned)ly < (unsigned)(E1 - 1) &&
-            (unsigned)lz < (unsigned)(E2 - 1)) {
-          const float* q = box + ((size_t)lx * E1 + ly) * E2 + lz;
-          const int sy = E2, sx = E1 * E2;
-          v = trilinear_interp<JAC>(q[0], q[1], q[sy], q[sy + 1], q[sx], q[sx + 1], q[sx + sy], q[sx + sy + 1],
-                                    cx - fx0, cy - fy0, cz - fz0, g);
-          ++n_shared;
-        } else {
-          v = sample_trilinear<JAC, false>(p.vol, cx, cy, cz, g);
-          ++n_global;
-        }
-        accumulate(cu, v, g);
-        have = false;
-        ++k;
+  // bounded wait for the bulk copies of a staged box; false (and `broken`) when the barrier does not complete
+  auto wait_box = [&](uint32_t bar_addr, uint32_t parity) -> bool {
+    if (broken) return false;
+    bool done = false;
+    for (int spin = 0; spin < (1 << 16) && !done; ++spin) done = mbar_try_wait(bar_addr, parity);
+    if (!done) {
+      broken = true;
+      ++n_timeout;
+    }
+    return done;
+  };
+
+  // ---- 3. this ray's samples whose cell lies in slab t, from `buf` when `staged`
+  auto march_slab = [&](int t, const BoxDesc& desc, const float* buf, bool staged) {
+    if (!regular) return;
+    const int bl0 = desc.lo[0], bl1 = desc.lo[1], bl2 = desc.lo[2];
+    const int E0 = desc.E[0], E1 = desc.E[1], E2 = desc.E[2];
+    while (k < np) {
+      if (!have) {
+        cu = linspace01(k, np, lstep);
+        const float alpha = fmaf(cu, span, ar.amin);
+        cx = fmaf(alpha, d[0], s[0]);
+        cy = fmaf(alpha, d[1], s[1]);
+        cz = fmaf(alpha, d[2], s[2]);
+        const float pa = A == 0 ? cx : (A == 1 ? cy : cz);
+        const int cs = slab_of((int)floorf(pa));
+        ct = forward ? cs : -cs;
+        have = true;
       }
+      if (ct > t) break;  // belongs to a later slab
+      float g[3], v;
+      const float fx0 = floorf(cx), fy0 = floorf(cy), fz0 = floorf(cz);
+      const int lx = (int)fx0 - bl0, ly = (int)fy0 - bl1, lz = (int)fz0 - bl2;
+      if (staged && ct == t && (unsigned)lx < (unsigned)(E0 - 1) && (unsigned)ly < (unsigned)(E1 - 1) &&
+          (unsigned)lz < (unsigned)(E2 - 1)) {
+        const float* q = buf + ((size_t)lx * E1 + ly) * E2 + lz;
+        const int sy = E2, sx = E1 * E2;
+        v = trilinear_interp<JAC>(q[0], q[1], q[sy], q[sy + 1], q[sx], q[sx + 1], q[sx + sy], q[sx + sy + 1],
+                                  cx - fx0, cy - fy0, cz - fz0, g);
+        ++n_shared;
+      } else {
+        v = sample_trilinear<JAC, false>(p.vol, cx, cy, cz, g);
+        ++n_global;
+      }
+      accumulate(cu, v, g);
+      have = false;
+      ++k;
+    }
+  };
+
+  if (STAGES == 1) {
+    // One buffer: publish -> barrier -> stage -> barrier + wait -> march.  Box descriptors are double-buffered so
+    // that warp 0 can publish slab t+1 while slower warps still copy slab t's descriptor into registers.
+    uint32_t phase = 0;
+    for (int t = tf; t <= tl; ++t) {
+      BoxDesc& desc = descs[(t - tf) & 1];
+      if (warp == 0) publish_box(t, desc);
+      __syncthreads();  // everyone is done with the previous slab's buffer; the new box is published
+      bool staged = desc.staged != 0;
+      if (staged) {  // CTA-uniform
+        stage_box(desc, box, bar);
+        __syncthreads();  // the zero fills are visible
+        staged = wait_box(bar, phase & 1u);
+        ++phase;
+      }
+      march_slab(t, desc, box, staged);
+    }
+  } else {
+    // Two buffers: while slab t is marched from buffer t&1, the bulk copies of slab t+1 fill buffer (t+1)&1.  One
+    // barrier per slab.  Descriptors live in three slots: slot (t+1)%3 is rewritten while slab t-1's readers are
+    // still possible only for slots (t-1)%3 and t%3.
+    uint32_t uses0 = 0u, uses1 = 0u;  // completed phases of each barrier
+    if (tf <= tl) {
+      if (warp == 0) publish_box(tf, descs[0]);
+      __syncthreads();
+      stage_box(descs[0], box, bar);
+    }
+    for (int t = tf; t <= tl; ++t) {
+      const int i = t - tf;
+      BoxDesc& desc = descs[i % 3];
+      BoxDesc& next = descs[(i + 1) % 3];
+      if (t < tl && warp == 0) publish_box(t + 1, next);
+      __syncthreads();  // slab t-1 fully marched (its buffer is free), slab t's zero fills and the next box visible
+      if (t < tl) stage_box(next, box + (size_t)((i + 1) & 1) * ST_CAP, bar + 8u * (uint32_t)((i + 1) & 1));
+      bool staged = desc.staged != 0;
+      if (staged) {
+        staged = wait_box(bar + 8u * (uint32_t)(i & 1), ((i & 1) ? uses1 : uses0) & 1u);
+        if (i & 1) ++uses1; else ++uses0;
+      }
+      march_slab(t, desc, box + (size_t)(i & 1) * ST_CAP, staged);
     }
   }
 
@@ -402,15 +445,16 @@ __global__ void __launch_bounds__(256, XVR_ST_MIN_CTAS) trilinear_fwd_staged_ker
 
 using namespace xvr;
 
-// Same arguments as xvr_trilinear_drr_fwd without the texture handle and tile shape, plus an optional device
-// counter triple `stats` = {samples served from shared memory, from global memory, barrier time-outs} the caller
-// zeroes.  Returns XVR_ERR_INVALID for what this variant does not cover (the caller then uses the texture kernel).
+// Same arguments as xvr_trilinear_drr_fwd without the texture handle and tile shape, plus `stages` (1: one staging
+// buffer, three CTAs per SM; 2: double-buffered, the copies of slab t+1 overlap the march of slab t, two CTAs per
+// SM) and an optional device counter triple `stats` = {samples served from shared memory, from global memory,
+// barrier time-outs} the caller zeroes.
 extern "C" int xvr_trilinear_drr_fwd_staged(const float* volume, int D0, int D1, int D2, const float* cam2vox,
                                             const float* cam2world, const float* det9, int B, int det_h, int det_w,
-                                            int n_points, int step_mode, float eps, float* out, float* jac,
+                                            int n_points, int step_mode, float eps, int stages, float* out, float* jac,
                                             unsigned long long* stats, void* stream) {
   if (!volume || !cam2vox || !cam2world || !det9 || !out || B <= 0 || det_h <= 0 || det_w <= 0 || D0 < 2 || D1 < 2 ||
-      D2 < 2 || n_points < 2 || step_mode < 0 || step_mode > 2) {
+      D2 < 2 || n_points < 2 || step_mode < 0 || step_mode > 2 || (stages != 1 && stages != 2)) {
     set_last_error("xvr_trilinear_drr_fwd_staged: invalid argument");
     return XVR_ERR_INVALID;
   }
@@ -450,14 +494,16 @@ extern "C" int xvr_trilinear_drr_fwd_staged(const float* volume, int D0, int D1,
     set_last_error("xvr_trilinear_drr_fwd_staged: grid too large");
     return XVR_ERR_INVALID;
   }
-  const int smem = ST_CAP * (int)sizeof(float);
+  const int smem = stages * ST_CAP * (int)sizeof(float);
   cudaStream_t st = (cudaStream_t)stream;
-  if (jac) {
-    cudaFuncSetAttribute(trilinear_fwd_staged_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    trilinear_fwd_staged_kernel<true><<<(unsigned)grid, 256, smem, st>>>(p);
+  auto launch = [&](auto kernel) {
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    kernel<<<(unsigned)grid, 256, smem, st>>>(p);
+  };
+  if (stages == 1) {
+    if (jac) launch(trilinear_fwd_staged_kernel<true, 1>); else launch(trilinear_fwd_staged_kernel<false, 1>);
   } else {
-    cudaFuncSetAttribute(trilinear_fwd_staged_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    trilinear_fwd_staged_kernel<false><<<(unsigned)grid, 256, smem, st>>>(p);
+    if (jac) launch(trilinear_fwd_staged_kernel<true, 2>); else launch(trilinear_fwd_staged_kernel<false, 2>);
   }
   return check_launch("xvr_trilinear_drr_fwd_staged");
 }

@@ -204,10 +204,12 @@ class _RenderDRR(torch.autograd.Function):
         if B == 0:  # an empty pose batch renders to an empty image batch; nothing to launch
             ctx.save_for_backward(jac)
             return out
-        if os.environ.get("XVR_B200_STAGED", "0") == "1":
-            # opt-in, not yet run on a GPU: bricks staged in shared memory by TMA bulk copies (csrc/trilinear_staged.cu)
+        staged = os.environ.get("XVR_B200_STAGED", "0")
+        if staged in ("1", "2"):
+            # opt-in, not yet run on a GPU: bricks staged in shared memory by TMA bulk copies, single (1) or double
+            # (2) buffered (csrc/trilinear_staged.cu)
             call("xvr_trilinear_drr_fwd_staged", ptr(volume), *volume.shape, ptr(cam2vox), ptr(cam2world), det, B, H, W,
-                 *args, ptr(out), ptr(jac), ptr(_staged_stats.get("tensor")), stream())
+                 *args, int(staged), ptr(out), ptr(jac), ptr(_staged_stats.get("tensor")), stream())
         else:
             call("xvr_trilinear_drr_fwd", ptr(volume), voltex, *volume.shape, ptr(cam2vox), ptr(cam2world), det, B, H,
                  W, *args, lw, cw, ptr(out), ptr(jac), stream())
