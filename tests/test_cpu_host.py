@@ -391,3 +391,41 @@ def test_checkpoint_round_trip_and_pose_prediction(tmp_path):
     shift = xvr_b200.convert(torch.zeros(1, 3), torch.tensor([[1.0, 2.0, 3.0]]), parameterization="euler_angles",
                              convention="ZXY")
     assert torch.allclose(correct_pose(pose_a, shift.matrix[0]).matrix, pose_a.compose(shift).matrix)
+
+
+def test_fused_registration_similarity_host_wiring(monkeypatch):
+    """Host side of xvr_regsim: weights, transform constants and workspace size reach the C-ABI as documented in
+    include/xvr_b200.h; the Registrar only selects it for the configuration it covers.  No kernel is launched."""
+    from xvr_b200 import metrics
+    from xvr_b200.registrar import Registrar
+
+    seen = {}
+
+    def fake_call(name, *args):
+        seen[name] = args
+
+    monkeypatch.setattr(metrics, "cuda_f32", lambda t, what: t.to(torch.float32).contiguous())
+    monkeypatch.setattr(metrics, "call", fake_call)
+    monkeypatch.setattr(metrics, "stream", lambda: None)
+    fixed = torch.rand(2, 1, 40, 48)
+    sim = metrics.RegistrationSimilarity(fixed, mncc_patch_size=9, gncc_patch_size=11, beta=0.3)
+    assert "xvr_sobel_fwd" in seen and sim.fixed_sobel.shape == (2, 2, 40, 48)
+    moving = torch.rand(2, 1, 40, 48, requires_grad=True)
+    score = sim(moving)
+    args = seen["xvr_regsim"]
+    B, H, W, std_eps, mean, inv_std, p, q, w_global, w_patch, w_grad, eps, _, n_work = args[3:17]
+    assert (B, H, W, p, q) == (2, 40, 48, 9, 11)
+    assert std_eps == pytest.approx(1e-6) and mean == pytest.approx(0.15) and inv_std == pytest.approx(10.0)
+    assert (w_global, w_patch, w_grad) == pytest.approx((0.15, 0.15, 0.7)) and eps == pytest.approx(conv.NCC_EPS)
+    assert n_work == _lib.lib().xvr_regsim_workspace_floats(2, 40, 48, 9, 11) > 0
+    assert score.shape == ()
+    (3.0 * score).backward()  # backward = saved gradient x upstream scalar (zeros here: nothing was launched)
+    assert moving.grad.shape == moving.shape
+    with pytest.raises(_lib.XvrB200Error):
+        metrics.RegistrationSimilarity(torch.rand(1, 1, 8, 8), 9, 11)(torch.rand(1, 1, 8, 8))
+
+    drr = object()
+    assert Registrar(drr, fused_similarity=True).fused_similarity
+    assert not Registrar(drr, fused_similarity=True, equalize=True).fused_similarity
+    assert not Registrar(drr, fused_similarity=True, sigma=1.0).fused_similarity
+    assert not Registrar(drr).fused_similarity
