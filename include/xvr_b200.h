@@ -129,7 +129,7 @@ int xvr_ncc_bwd(const float* x1, const float* x2, const float* coef, int which, 
 int xvr_sobel_fwd(const float* x, int B, int H, int W, float* out /* (B,2,H,W) */, void* stream);
 int xvr_sobel_bwd(const float* gout, int B, int H, int W, float* gx /* (B,1,H,W) */, void* stream);
 
-/* ---- Value and gradient of the registration similarity in nine launches: the chain
+/* ---- Value and gradient of the registration similarity in nine launches (parity-green on the B200): the chain
  *   XrayTransforms(moving) -> beta * mNCC([None, p]) + (1 - beta) * GradNCC(q, sigma = 0) -> .sum() -> backward
  * of /root/reference/src/xvr/registrar/base.py:245-252 (transform: utils/preprocess.py:5-29, no Equalize, no resize).
  *   fixed (B,1,H,W) the transformed target, fixed_sobel (B,2,H,W) = xvr_sobel_fwd(fixed), moving (B,1,H,W) raw DRRs;

@@ -47,7 +47,7 @@ for b in range(len(EDGE_ROT)):
         rz=np.abs(row[2]).sum()
         j0,j1,i0,i1=0,W-1,0,H-1
         skip=False
-        if q[2]>8*rz:
+        if False:  # the linearised window was dropped: the projected-corner box is used for every voxel
             m=SDD/q[2]; cj=(q[0]*m-o[0])/v[0]; ci=(q[1]*m-o[1])/u[1]
             rj=sum(abs(row[0][a]-(q[0]/q[2])*row[2][a]) for a in range(3))*m*abs(1/v[0])*1.01+1e-3
             ri=sum(abs(row[1][a]-(q[1]/q[2])*row[2][a]) for a in range(3))*m*abs(1/u[1])*1.01+1e-3

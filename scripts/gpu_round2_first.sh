@@ -2,7 +2,7 @@
 #   gpurun --timeout 600 -- 'bash scripts/gpu_round2_first.sh'
 set -x
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_zzz_unrun_gpu.py -m gpu -q -rxX --runxfail 2>&1 | tail -40
+timeout 300 python -m pytest tests/test_zzz_unrun_gpu.py tests/test_regsim_gpu.py -m gpu -q -rxX --runxfail 2>&1 | tail -40
 # the staged-brick kernel waits on an mbarrier: first run under its own short timeout
 XVR_B200_RUN_UNVALIDATED=1 timeout 120 python -m pytest tests/test_zzz_unrun_gpu.py -m gpu -q -k staged --runxfail 2>&1 | tail -40
 for S in 1 2; do

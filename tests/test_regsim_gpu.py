@@ -1,0 +1,67 @@
+"""xvr_regsim -- value and gradient of the registration similarity in nine launches (csrc/ncc.cu) --
+against the composition it replaces, and the registration loop with it switched on.  Passed on the B200 at the end
+of round 1; the Registrar keeps it opt-in (``fused_similarity=True``) until it has been timed."""
+
+import pytest
+import torch
+
+import xvr_b200
+from tests._scene import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("B,H,W", [(1, 64, 64), (3, 40, 33)])
+def test_fused_registration_similarity_matches_the_composition(cuda, B, H, W):
+    """xvr_regsim (value + gradient, nine launches) against XrayTransforms -> beta mNCC + (1 - beta) GradNCC ->
+    .sum() -> autograd built from the unfused modules, on images with ties at the minimum (DRR background) and at
+    the maximum."""
+    from xvr_b200.metrics import (GradientNormalizedCrossCorrelation2d, MultiscaleNormalizedCrossCorrelation2d,
+                                  RegistrationSimilarity)
+    from xvr_b200.preprocess import XrayTransforms
+
+    g = torch.Generator().manual_seed(7)
+    transform = XrayTransforms(H, W)
+    fixed = transform((torch.rand(B, 1, H, W, generator=g) * 5.0).to(cuda))
+    moving = (torch.rand(B, 1, H, W, generator=g) * 3.0).to(cuda)
+    moving[:, :, :6, :7] = 0.0
+    moving[0, 0, 10, 10] = moving[-1, 0, 20, 5] = 4.0
+    beta = 0.3
+    sim1 = MultiscaleNormalizedCrossCorrelation2d([None, 9], [0.5, 0.5])
+    sim2 = GradientNormalizedCrossCorrelation2d(11, sigma=0.0).to(cuda)
+
+    m1 = moving.clone().requires_grad_()
+    y = transform(m1)
+    ref = (beta * sim1(fixed, y) + (1 - beta) * sim2(fixed, y)).sum()
+    ref.backward()
+
+    m2 = moving.clone().requires_grad_()
+    out = RegistrationSimilarity(fixed, 9, 11, beta=beta)(m2)
+    (2.0 * out).backward()
+    assert out.shape == ()
+    assert abs(out.item() - ref.item()) < 1e-5 * max(1.0, abs(ref.item()))
+    assert rel_l2(m2.grad, 2.0 * m1.grad) < 1e-4
+    assert (m2.grad - 2.0 * m1.grad).abs().max().item() < 1e-4 * (2.0 * m1.grad).abs().max().item()
+
+
+def test_registrar_with_fused_similarity_follows_the_unfused_trajectory(cuda):
+    from tests._scene import make_drr
+    from xvr_b200.registrar import Registrar
+
+    res = []
+    for fused in (False, True):
+        drr = make_drr(96, 64)
+        rot0 = torch.tensor([[0.20, -0.10, 0.05]], device=cuda)
+        xyz0 = torch.tensor([[5.0, 800.0, -10.0]], device=cuda)
+        with torch.no_grad():
+            gt = drr(xvr_b200.convert(rot0, xyz0, parameterization="euler_angles", convention="ZXY"))
+        init = xvr_b200.convert(rot0 + torch.tensor([[0.06, -0.05, 0.04]], device=cuda),
+                                xyz0 + torch.tensor([[8.0, 12.0, -6.0]], device=cuda),
+                                parameterization="euler_angles", convention="ZXY")
+        pose, info = Registrar(drr, scales="1", n_itrs="60", fused_similarity=fused).run(gt, init)
+        res.append((pose.matrix.clone(), info))
+    a, b = res[0][1]["nccs"], res[1][1]["nccs"]
+    assert len(a) == len(b)
+    assert max(abs(u - v) for u, v in zip(a, b)) < 2e-3
+    assert b[-1] > b[0]
+    assert (res[0][0] - res[1][0]).abs().max().item() < 0.5  # mm / unit rotation entries

@@ -228,10 +228,12 @@ def volgrad_version(request):
     call("xvr_set_volgrad_version", 2)  # the library default
 
 
-@pytest.mark.parametrize("volgrad_version", [1, 2], indirect=True)
+# version 1 (the voxel-centric gather kept as a cross-check) was last changed after its last GPU run: its turn at
+# these cases is in tests/test_zzz_unrun_gpu.py
+@pytest.mark.parametrize("volgrad_version", [2], indirect=True)
 @pytest.mark.parametrize("n,h,b", [(24, 16, 3), (40, 33, 2), (50, 64, 2)])
 def test_volume_gradient_matches_oracle_and_is_deterministic(cuda, n, h, b, volgrad_version):
-    """dL/dvolume (atomics-free: brick-local scatter, or the voxel-centric gather kept as a cross-check) vs autograd through
+    """dL/dvolume (atomics-free brick-local scatter) vs autograd through
     grid_sample's atomicAdd scatter."""
     import oracle
 

@@ -264,11 +264,13 @@ def test_config5_is_bit_reproducible(config5):
 
 
 # ------------------------------------------------------------------------------------------ dL/dvolume, edge geometry
-@pytest.fixture(params=[1, 2], ids=["gather", "brick"])
+# The library default (brick-local scatter).  The gather kernel (version 1) was last changed after its last GPU run;
+# its turn at these cases is in tests/test_zzz_unrun_gpu.py.
+@pytest.fixture(params=[2], ids=["brick"])
 def volgrad_version(request):
     call("xvr_set_volgrad_version", request.param)
     yield request.param
-    call("xvr_set_volgrad_version", 2)  # the library default
+    call("xvr_set_volgrad_version", 2)
 
 
 def _volume_gradient_vs_oracle(drr, rot, xyz):
@@ -299,13 +301,15 @@ def _volume_gradient_vs_oracle(drr, rot, xyz):
 def test_volume_gradient_anisotropic_voxels_offset_reversed_detector(cuda, volgrad_version):
     """Non-cubic volume with three different spacings, non-square detector with non-square pixels, shifted
     principal point, reversed column axis: the geometry terms of the ray-separation bound of the brick kernel."""
+    _volume_gradient_vs_oracle(_anisotropic_drr(cuda), *pose_params(3, seed=5))
+
+
+def _anisotropic_drr(device):
     g = torch.Generator().manual_seed(3)
     vol = torch.rand(40, 64, 52, generator=g) * 1000 - 500
     sub = read(vol, affine=np.diag([2.0, 1.5, 2.5, 1.0]))
-    drr = xvr_b200.DRR(sub, 1020.0, 24, 6.0, width=40, dely=5.0, x0=7.0, y0=-11.0, renderer="trilinear",
-                       reverse_x_axis=True).to(cuda)
-    rot, xyz = pose_params(3, seed=5)
-    _volume_gradient_vs_oracle(drr, rot, xyz)
+    return xvr_b200.DRR(sub, 1020.0, 24, 6.0, width=40, dely=5.0, x0=7.0, y0=-11.0, renderer="trilinear",
+                        reverse_x_axis=True).to(device)
 
 
 EDGE_ROT = [[0.0, 0.0, 0.0], [0.0, 0.0, 0.0], [1.2, 0.3, 0.0], [0.0, 0.0, 0.0], [0.0, 1.5707964, 0.0]]

@@ -75,50 +75,34 @@ __global__ void __launch_bounds__(256) volume_grad_kernel(const VolGradParams p)
       for (int c = 0; c < 3; ++c) row[a][c] = __ldg(Gi + a * 4 + c);
       q[a] = fmaf(row[a][2], pv[2], fmaf(row[a][1], pv[1], fmaf(row[a][0], pv[0], __ldg(Gi + a * 4 + 3))));
     }
-    // Candidate rays = pixel window of the voxel's +-1 support.  rz is the depth half-extent of that support.
-    const float rz = fabsf(row[2][0]) + fabsf(row[2][1]) + fabsf(row[2][2]);
+    // Candidate rays = pixel box of the 8 projected corners of the voxel's +-1 support (a convex set in front of the
+    // source projects inside the box of its projected vertices).  A support that reaches the source plane has no
+    // finite window -- every ray is a candidate (voxels around a source placed inside the volume: every ray's first
+    // sample, alpha = 0, is the source itself) -- and one entirely behind the source is never reached.
+    // (Until the end of round 1 the window came from the projection linearised at the voxel centre with 1 % of
+    // padding: only a bound when the support's depth is < 1 % of the voxel's, and voxels behind the source plane were
+    // skipped -- 6 % off with the source inside the volume, 3e-4 off after a partial fix; scripts/check_gather_window.py.)
+    float jmin = INFINITY, jmax = -INFINITY, imin = INFINITY, imax = -INFINITY;
+    int in_front = 0;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const float sx = (c & 1) ? 1.f : -1.f, sy = (c & 2) ? 1.f : -1.f, sz = (c & 4) ? 1.f : -1.f;
+      const float q0 = q[0] + sx * row[0][0] + sy * row[0][1] + sz * row[0][2];
+      const float q1 = q[1] + sx * row[1][0] + sy * row[1][1] + sz * row[1][2];
+      const float q2 = q[2] + sx * row[2][0] + sy * row[2][1] + sz * row[2][2];
+      if (q2 > 1e-3f * sdd) {
+        const float m = sdd / q2;
+        const float cj = (q0 * m - p.geom.o[0]) * inv_vx, ci = (q1 * m - p.geom.o[1]) * inv_uy;
+        jmin = fminf(jmin, cj); jmax = fmaxf(jmax, cj);
+        imin = fminf(imin, ci); imax = fmaxf(imax, ci);
+        ++in_front;
+      }
+    }
+    if (in_front == 0) continue;  // behind the source
     int j0 = 0, j1 = p.W - 1, i0 = 0, i1 = p.H - 1;
-    if (q[2] > 8.f * rz) {
-      // far from the source plane: window from the projection linearised at the voxel centre, padded by 1 %
-      const float m = sdd / q[2];
-      const float cj = (q[0] * m - p.geom.o[0]) * inv_vx;
-      const float ci = (q[1] * m - p.geom.o[1]) * inv_uy;
-      float rj = 0.f, ri = 0.f;
-#pragma unroll
-      for (int a = 0; a < 3; ++a) {
-        rj += fabsf(row[0][a] - (q[0] / q[2]) * row[2][a]);
-        ri += fabsf(row[1][a] - (q[1] / q[2]) * row[2][a]);
-      }
-      rj = rj * m * fabsf(inv_vx) * 1.01f + 1e-3f;
-      ri = ri * m * fabsf(inv_uy) * 1.01f + 1e-3f;
-      j0 = max(0, (int)ceilf(cj - rj)); j1 = min(p.W - 1, (int)floorf(cj + rj));
-      i0 = max(0, (int)ceilf(ci - ri)); i1 = min(p.H - 1, (int)floorf(ci + ri));
-    } else {
-      // near the source (a source inside or next to the volume) the linearisation is no bound: take the pixel box of
-      // the 8 projected corners of the support (a convex set in front of the source projects inside the box of its
-      // projected vertices); a support that reaches the source plane has no finite window -- every ray is a
-      // candidate -- and one entirely behind the source is never reached.
-      float jmin = INFINITY, jmax = -INFINITY, imin = INFINITY, imax = -INFINITY;
-      int in_front = 0;
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const float sx = (c & 1) ? 1.f : -1.f, sy = (c & 2) ? 1.f : -1.f, sz = (c & 4) ? 1.f : -1.f;
-        const float q0 = q[0] + sx * row[0][0] + sy * row[0][1] + sz * row[0][2];
-        const float q1 = q[1] + sx * row[1][0] + sy * row[1][1] + sz * row[1][2];
-        const float q2 = q[2] + sx * row[2][0] + sy * row[2][1] + sz * row[2][2];
-        if (q2 > 1e-3f * sdd) {
-          const float m = sdd / q2;
-          const float cj = (q0 * m - p.geom.o[0]) * inv_vx, ci = (q1 * m - p.geom.o[1]) * inv_uy;
-          jmin = fminf(jmin, cj); jmax = fmaxf(jmax, cj);
-          imin = fminf(imin, ci); imax = fmaxf(imax, ci);
-          ++in_front;
-        }
-      }
-      if (in_front == 0) continue;  // behind the source
-      if (in_front == 8) {
-        j0 = max(0, (int)ceilf(jmin - 1e-3f)); j1 = min(p.W - 1, (int)floorf(jmax + 1e-3f));
-        i0 = max(0, (int)ceilf(imin - 1e-3f)); i1 = min(p.H - 1, (int)floorf(imax + 1e-3f));
-      }
+    if (in_front == 8) {
+      j0 = max(0, (int)ceilf(jmin - 1e-3f)); j1 = min(p.W - 1, (int)floorf(jmax + 1e-3f));
+      i0 = max(0, (int)ceilf(imin - 1e-3f)); i1 = min(p.H - 1, (int)floorf(imax + 1e-3f));
     }
     if (i0 > i1 || j0 > j1) continue;
     // the source is the translation column of cam2vox (what generate_ray uses)
