@@ -112,6 +112,12 @@ int xvr_siddon_trace(const float* volume, int D0, int D1, int D2, const float* s
  * a huge value, e.g. 1e30, routes every segment through the reference's exact normalise/un-normalise arithmetic) */
 int xvr_set_siddon_index_tol_scale(float scale);
 
+/* opt-in (NOT yet run on a GPU): 1 = the forward (without label channels) and trace kernels take the voxel index of
+ * a segment from an integer walk whenever min_a |d_a| * segment length / 2 exceeds the rounding budget of the
+ * certified index -- one multiply + compare instead of the three-axis evaluation, same indices
+ * (scripts/siddon_cheap_certificate.py); 0 = default */
+int xvr_set_siddon_walk(int on);
+
 /* test hook: the hoisted-reciprocal division of the traversal vs IEEE division on random operands;
  * mismatches is a DEVICE counter the caller zeroes */
 int xvr_selftest_division(int blocks, int per_thread, unsigned seed, unsigned long long* mismatches, void* stream);

@@ -125,3 +125,55 @@ def test_staged_bricks_edge_poses_and_partial_tiles(cuda, monkeypatch, stages):
         assert all(torch.equal(u, v) for u, v in zip(a[:3], b[:3])) and b[3][2] == 0
         if shape[2] % 4:
             assert b[3][0] == 0  # rows of 50 floats cannot be bulk-copied: everything comes from global memory
+
+
+# ------------------------------------------------------------------------------------------ Siddon integer walk
+@pytest.fixture
+def siddon_walk():
+    call("xvr_set_siddon_walk", 1)
+    yield
+    call("xvr_set_siddon_walk", 0)
+
+
+@_UNRUN
+@pytest.mark.parametrize("n,h,b,shift", [(64, 48, 4, 0.5), (40, 33, 3, 0.0), (256, 128, 2, 0.5)])
+def test_siddon_walk_traversal_is_bit_exact(cuda, siddon_walk, n, h, b, shift):
+    """xvr_set_siddon_walk(1): indices from the integer walk + one-compare certificate, against the oracle's
+    reconstruction of the reference's indices (same assertions as test_siddon_gpu.test_traversal_is_bit_exact)."""
+    import oracle
+    from tests._scene import make_drr, pose_params
+    from tests.test_siddon_gpu import _rays, _trace
+
+    drr = make_drr(n, h, renderer="siddon", voxel_shift=shift)
+    rot, xyz = pose_params(b, seed=11)
+    source, target, _ = _rays(drr, rot, xyz)
+    ref_idx, ref_seg = oracle.siddon_segments(tuple(drr.density.shape), source, target, voxel_shift=shift)
+    M = ref_idx.shape[-1]
+    idx, seg, cnt = _trace(drr.density, source, target, shift, M + 8)
+    ref_valid = torch.diff(oracle.siddon_alphas(source, target, tuple(drr.density.shape), shift, 1e-8), dim=-1)
+    ref_cnt = (~ref_valid.isnan()).sum(-1).to(torch.int32)
+    assert torch.equal(cnt, ref_cnt)
+    live = torch.arange(M, device=cuda)[None, None] < ref_cnt[..., None]
+    pos = live & (ref_seg > 0)  # ties between axes may be emitted in either order: zero-length segments are exempt
+    assert torch.equal(seg[..., :M][live], ref_seg[live])
+    assert torch.equal(idx[..., :M][pos].long(), ref_idx[pos])
+
+
+@_UNRUN
+def test_siddon_walk_renders_bit_identical_images_and_gradients(cuda):
+    from tests._scene import make_drr, pose_params
+
+    drr = make_drr(128, 64, renderer="siddon")
+    rot, xyz = pose_params(3, seed=3)
+    outs = []
+    for on in (0, 1):
+        call("xvr_set_siddon_walk", on)
+        try:
+            r, x = rot.clone().requires_grad_(), xyz.clone().requires_grad_()
+            img = drr(xvr_b200.convert(r, x, parameterization="euler_angles", convention="ZXY"))
+            img.sum().backward()
+            outs.append((img.detach().clone(), r.grad.clone(), x.grad.clone()))
+        finally:
+            call("xvr_set_siddon_walk", 0)
+    for u, v in zip(*outs):
+        assert torch.equal(u, v)

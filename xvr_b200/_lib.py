@@ -41,6 +41,7 @@ _SIGNATURES = {
     "xvr_set_ksplit": ([c_int], c_int),
     "xvr_set_volgrad_version": ([c_int], c_int),
     "xvr_set_siddon_index_tol_scale": ([c_float], c_int),
+    "xvr_set_siddon_walk": ([c_int], c_int),
     "xvr_rays_jac_bwd": ([P, P, c_int, c_int, P, P, P, P, P], c_int),
     "xvr_ncc_fwd": ([P, P, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_int, P, P, P, P, P], c_int),
     "xvr_ncc_bwd": ([P, P, P, c_int, P, c_int, c_int, c_int, c_int, c_int, c_float, c_int, P, P], c_int),
