@@ -65,6 +65,11 @@ def test_invalid_arguments_return_error_codes_not_crashes():
     assert lib.xvr_regsim(None, None, None, 1, 256, 256, 1e-6, 0.15, 10.0, 9, 11, 0.25, 0.25, 0.5, 1e-5, None, n, None,
                           None, None) == -1
     assert b"xvr_regsim" in lib.xvr_last_error()
+    # staged-brick renderer: one or two staging buffers, nothing else
+    assert lib.xvr_trilinear_drr_fwd_staged(None, 8, 8, 8, None, None, None, 1, 16, 16, 10, 0, 1e-8, 1, None, None, None,
+                                            None) == -1
+    assert b"xvr_trilinear_drr_fwd_staged" in lib.xvr_last_error()
+    assert lib.xvr_set_siddon_walk(0) == 0 and lib.xvr_set_volgrad_version(3) == -1
 
 
 def test_product_never_imports_the_oracle():
