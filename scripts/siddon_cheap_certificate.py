@@ -10,7 +10,7 @@ Round 1 (256^3, 96 x 96 rays, 4 bench poses, 12.1 M segments): 98.86 % certified
 630 uncertified segments do differ from the exact-arithmetic cell -- exactly the grazing cases left to today's path.
     PYTHONPATH=. python scripts/siddon_cheap_certificate.py
 """
-import torch, numpy as np, oracle
+import torch, oracle
 from tests._scene import pixel_size
 from bench import pose_batch
 N=256; H=W=96; SDD=1020.0

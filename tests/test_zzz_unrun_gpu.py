@@ -14,7 +14,6 @@ import pytest
 import torch
 
 import xvr_b200
-from tests._scene import rel_l2
 from tests.test_zz_full_size_gpu import EDGE_ROT, EDGE_XYZ, _volume_gradient_vs_oracle
 from xvr_b200._lib import call
 
