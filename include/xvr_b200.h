@@ -21,6 +21,15 @@
 extern "C" {
 #endif
 
+/* Per-call options word: the last argument before `stream` of every entry point that has variants.  0 = the
+ * library default; unknown bits are an invalid argument.  (ABI 1 had process-global setters for these.) */
+#define XVR_OPT_KSPLIT(log2) ((log2) + 1) /* trilinear forward: 2^log2 (0..3) lanes share one ray; 0 in the field = automatic
+                                           * (small batches, B = 1 registration, split rays so that the SMs stay full) */
+#define XVR_OPT_SIDDON_CHECKED 0x10       /* Siddon: certified evaluation of every voxel index instead of the integer walk */
+#define XVR_OPT_VOLGRAD_GATHER 0x20       /* dL/dvolume: voxel-centric gather (cross-check) instead of the brick-local scatter */
+#define XVR_OPT_SIDDON_TOL(code) ((code) << 8) /* test hook: tolerance of the fast voxel-index certificate; 0 production,
+                                           * 1 always the reference's exact arithmetic, 2/3/4 = x 1/2, 1/4, 1/8 (margin probes) */
+
 int xvr_abi_version(void);
 const char* xvr_last_error(void);
 /* kernels launched by this library since it was loaded */
@@ -42,7 +51,7 @@ int xvr_volume_destroy(void* handle);
 int xvr_trilinear_rays_fwd(const float* volume, const void* voltex, int D0, int D1, int D2, const uint8_t* labels,
                            int C, const float* source, const float* target, const float* raylen, int B, int N,
                            int n_points, int step_mode, float eps, int det_h, int det_w, int lane_w_log2,
-                           int cta_w_log2, float* out, float* jac, void* stream);
+                           int cta_w_log2, float* out, float* jac, int opts, void* stream);
 /* autograd backward of the above (= grid_sample backward + glue): re-marches the rays.
  *   gout (B,C,N) -> gsource (B,1,3), gtarget (B,N,3), graylen (B,N); workspace (B,3,N) */
 int xvr_trilinear_rays_bwd(const float* volume, const void* voltex, int D0, int D1, int D2, const uint8_t* labels,
@@ -50,9 +59,6 @@ int xvr_trilinear_rays_bwd(const float* volume, const void* voltex, int D0, int 
                            int n_points, int step_mode, float eps, int det_h, int det_w, int lane_w_log2,
                            int cta_w_log2, const float* gout, float* gsource, float* gtarget, float* graylen,
                            float* workspace, void* stream);
-/* lanes sharing one ray in the trilinear forward kernels, as log2 (0..3), -1 = automatic: small batches (B = 1
- * registration) split each ray's samples over several lanes so that the SMs stay full */
-int xvr_set_ksplit(int ks_log2);
 /* backward through a Jacobian saved by a *_rays_fwd call: 28 bytes per ray instead of a second march */
 int xvr_rays_jac_bwd(const float* jac, const float* gout, int B, int N, float* gsource, float* gtarget,
                      float* graylen, float* workspace, void* stream);
@@ -65,7 +71,7 @@ int xvr_rays_jac_bwd(const float* jac, const float* gout, int B, int N, float* g
 int xvr_trilinear_drr_fwd(const float* volume, const void* voltex, int D0, int D1, int D2, const float* cam2vox,
                           const float* cam2world, const float* det9, int B, int det_h, int det_w, int n_points,
                           int step_mode, float eps, int lane_w_log2, int cta_w_log2, float* out, float* jac,
-                          void* stream);
+                          int opts, void* stream);
 /* gG (B,3,4) = dL/d cam2vox from the saved Jacobian and gout (B,1,H*W).  workspace: NULL, or
  * 12 * B * xvr_drr_jac_bwd_slices(B, H*W) floats so that small batches spread each pose over several CTAs */
 int xvr_drr_jac_bwd_slices(int B, int N);
@@ -78,7 +84,7 @@ int xvr_drr_jac_bwd(const float* jac, const float* gout, const float* det9, int 
 int xvr_trilinear_drr_bwd_volume(const float* cam2vox, const float* vox2cam, const float* cam2world,
                                  const float* det9, int B, int det_h, int det_w, int n_points, int step_mode,
                                  float eps, const float* gout, int D0, int D1, int D2, float* workspace, float* gvol,
-                                 int accumulate, void* stream);
+                                 int accumulate, int opts, void* stream);
 /* Opt-in variant of xvr_trilinear_drr_fwd (NOT yet run on a GPU, csrc/trilinear_staged.cu): 16x16 detector tiles
  * march the volume slab by slab, each slab's brick staged in shared memory by cp.async.bulk (TMA) behind an mbarrier;
  * same arithmetic and summation order, so out / jac are bit-identical to xvr_trilinear_drr_fwd.  stages: 1 = one
@@ -88,35 +94,36 @@ int xvr_trilinear_drr_fwd_staged(const float* volume, int D0, int D1, int D2, co
                                  const float* cam2world, const float* det9, int B, int det_h, int det_w, int n_points,
                                  int step_mode, float eps, int stages, float* out, float* jac,
                                  unsigned long long* stats, void* stream);
-/* formulation of the volume gradient: 2 = brick-local scatter in shared memory (default), 1 = voxel-centric gather
- * (independent cross-check); both atomics-free and deterministic, same result (csrc/volgrad.cu) */
-int xvr_set_volgrad_version(int version);
+/* (two formulations, both atomics-free and deterministic, same result: brick-local scatter in shared memory by
+ * default, voxel-centric gather with XVR_OPT_VOLGRAD_GATHER; csrc/volgrad.cu) */
 
 /* ---- Siddon renderer = diffdrr.renderers.Siddon.forward (same call sites, --renderer siddon)
  * Traversed voxel indices are bit-identical to the reference's sort + grid_sample(nearest) formulation. */
 int xvr_siddon_rays_fwd(const float* volume, int D0, int D1, int D2, const uint8_t* labels, int C,
                         const float* source, const float* target, const float* raylen, int B, int N,
                         float voxel_shift, float eps, int det_h, int det_w, int lane_w_log2, int cta_w_log2,
-                        float* out, float* jac, void* stream);
+                        float* out, float* jac, int opts, void* stream);
+/* fused Siddon DRR = diffdrr.drr.DRR.forward with renderer="siddon" (registrar/base.py:249, trainer.py:283-289 with
+ * --renderer siddon): rays generated in-kernel as in xvr_trilinear_drr_fwd, out (B,1,H*W), jac (B,7,H*W) or NULL;
+ * backward = xvr_drr_jac_bwd */
+int xvr_siddon_drr_fwd(const float* volume, int D0, int D1, int D2, const float* cam2vox, const float* cam2world,
+                       const float* det9, int B, int det_h, int det_w, float voxel_shift, float eps, int lane_w_log2,
+                       int cta_w_log2, float* out, float* jac, int opts, void* stream);
 int xvr_siddon_rays_bwd(const float* volume, int D0, int D1, int D2, const uint8_t* labels, int C,
                         const float* source, const float* target, const float* raylen, int B, int N,
                         float voxel_shift, float eps, int det_h, int det_w, int lane_w_log2, int cta_w_log2,
                         const float* gout, float* gsource, float* gtarget, float* graylen, float* workspace,
-                        void* stream);
-/* test hook: the traversal itself. idx/seg (B,N,trace_max), count (B,N) */
+                        int opts, void* stream);
+/* the traversal itself (test hook, and bench.py's segment count): idx/seg (B,N,trace_max), count (B,N);
+ * trace_max = 0 with idx = seg = NULL writes the per-ray segment counts only */
 int xvr_siddon_trace(const float* volume, int D0, int D1, int D2, const float* source, const float* target, int B,
                      int N, float voxel_shift, float eps, int trace_max, int32_t* idx, float* seg, int32_t* count,
-                     void* stream);
-
-/* test hook: scale of the per-ray tolerance that certifies the fast voxel index of the traversal (1 = production;
- * a huge value, e.g. 1e30, routes every segment through the reference's exact normalise/un-normalise arithmetic) */
-int xvr_set_siddon_index_tol_scale(float scale);
-
-/* opt-in (NOT yet run on a GPU): 1 = the forward (without label channels) and trace kernels take the voxel index of
- * a segment from an integer walk whenever min_a |d_a| * segment length / 2 exceeds the rounding budget of the
- * certified index -- one multiply + compare instead of the three-axis evaluation, same indices
- * (scripts/siddon_cheap_certificate.py); 0 = default */
-int xvr_set_siddon_walk(int on);
+                     int opts, void* stream);
+/* Voxel index of a segment: by default the forward (without label channels) and trace kernels take it from an integer
+ * walk (+-stride at every plane crossing) whenever min_a |d_a| * segment length / 2 exceeds the rounding budget of the
+ * certified evaluation -- one multiply + compare instead of the three-axis evaluation, provably the same index
+ * (scripts/siddon_cheap_certificate.py; bit-exact on the B200 against the oracle's reconstruction of the reference's
+ * indices, tests/test_siddon_gpu.py).  XVR_OPT_SIDDON_CHECKED evaluates every index the certified way. */
 
 /* test hook: the hoisted-reciprocal division of the traversal vs IEEE division on random operands;
  * mismatches is a DEVICE counter the caller zeroes */
@@ -163,6 +170,20 @@ int xvr_euler_camera_fwd(const float* rot, const float* xyz, int B, const int* a
 int xvr_euler_camera_bwd(const float* rot, const float* xyz, int B, const int* axes, int rotated_frame,
                          const float* reorient16, const float* affinv16, const float* gcam2vox, float* grot,
                          float* gxyz, void* stream);
+/* xvr_pose_*: the same for every closed-form parameterisation of diffdrr.pose.convert (call sites
+ *   /root/reference/src/xvr/model/network.py:49-54 -- the regressor head, quaternion_adjugate by default,
+ *   config/trainer.py:17 --, model/sampler.py:29-31, registrar/base.py:168-170), one launch each way.
+ *   kind 0..6 = euler_angles, axis_angle, so3_log_map, se3_log_map, quaternion, rotation_6d, quaternion_adjugate with
+ *   n_rot = 3,3,3,3,4,6,10; rot (B,n_rot), xyz (B,3); axes HOST int[3] (Euler only, else NULL); angle_scale = pi/180 for
+ *   degrees=True (Euler only); reorient16 / affinv16 HOST 4x4 or both NULL.  Outputs (any may be NULL): pose (B,4,4),
+ *   cam2world, cam2vox (B,3,4; need the camera constants).  Backward: gpose (B,4,4) and/or gcam2vox (B,3,4) -> grot, gxyz
+ *   (one thread per pose and parameter, forward-mode differentiation of the forward's own code). */
+int xvr_pose_fwd(const float* rot, const float* xyz, int B, int kind, int n_rot, const int* axes, int rotated_frame,
+                 float angle_scale, const float* reorient16, const float* affinv16, float* pose, float* cam2world,
+                 float* cam2vox, void* stream);
+int xvr_pose_bwd(const float* rot, const float* xyz, int B, int kind, int n_rot, const int* axes, int rotated_frame,
+                 float angle_scale, const float* reorient16, const float* affinv16, const float* gpose,
+                 const float* gcam2vox, float* grot, float* gxyz, void* stream);
 int xvr_reg_update(float* rot, float* xyz, const float* grot, const float* gxyz, int n_rot, float* m_rot, float* v_rot,
                    float* m_xyz, float* v_xyz, double* state8, const float* loss, float* log_rows, float* log_count,
                    int max_rows, const double* hyper9, void* stream);

@@ -42,7 +42,7 @@ def test_library_exports_every_declared_symbol():
     assert len(protos) >= 19
     for name in protos:
         assert hasattr(handle, name), f"{name} declared in include/xvr_b200.h but not exported"
-    assert handle.xvr_abi_version() == 1
+    assert handle.xvr_abi_version() == 2
 
 
 def test_bindings_match_header_arity():
@@ -69,7 +69,10 @@ def test_invalid_arguments_return_error_codes_not_crashes():
     assert lib.xvr_trilinear_drr_fwd_staged(None, 8, 8, 8, None, None, None, 1, 16, 16, 10, 0, 1e-8, 1, None, None, None,
                                             None) == -1
     assert b"xvr_trilinear_drr_fwd_staged" in lib.xvr_last_error()
-    assert lib.xvr_set_siddon_walk(0) == 0 and lib.xvr_set_volgrad_version(3) == -1
+    # per-call options: unknown bits and out-of-range fields are invalid arguments, checked before any device work
+    assert lib.xvr_siddon_drr_fwd(None, 8, 8, 8, None, None, None, 1, 16, 16, 0.5, 1e-8, 0, 3, None, None, 0, None) == -1
+    assert b"xvr_siddon_drr_fwd" in lib.xvr_last_error()
+    assert lib.xvr_abi_version() == 2
 
 
 def test_product_never_imports_the_oracle():
@@ -434,3 +437,87 @@ def test_fused_registration_similarity_host_wiring(monkeypatch):
     assert not Registrar(drr, fused_similarity=True, equalize=True).fused_similarity
     assert not Registrar(drr, fused_similarity=True, sigma=1.0).fused_similarity
     assert not Registrar(drr).fused_similarity
+
+
+# ------------------------------------------------------------------------------------------------ round-2 additions
+def test_label_cache_is_keyed_by_tensor_identity_not_by_address():
+    """The reference's Trainer.load builds a fresh float mask per iteration; the allocator reuses the block, so
+    pointer + shape + version 0 repeat for a DIFFERENT label map.  The cache must not serve the old entry."""
+    from xvr_b200.renderers import _LabelCache
+
+    cache = _LabelCache()
+    a = torch.zeros(4, 4, 4)
+    a[0, 0, 0] = 3.0
+    lab_a, c_a = cache.get(a)
+    assert c_a == 4 and cache.get(a)[0] is lab_a  # same object: a hit
+    key = next(iter(cache.entries))
+    del a
+    b = torch.zeros(4, 4, 4)
+    b[1, 1, 1] = 7.0
+    # force the collision the allocator produces on the GPU: file b under a's key
+    entry = cache.entries.pop(key)
+    cache.entries[(b.data_ptr(), b._version, tuple(b.shape), b.dtype, b.device)] = entry
+    lab_b, c_b = cache.get(b)
+    assert c_b == 8 and lab_b[1, 1, 1] == 7 and lab_b is not lab_a
+
+
+def test_registrar_save_writes_the_reference_schema(tmp_path):
+    """parameters.pt carries the keys of the reference's _RegistrarBase.save (registrar/base.py:355-394) and
+    round-trips; B != 1 is rejected before any device work."""
+    from tests._scene import make_subject
+    from xvr_b200.registrar import Registrar
+
+    drr = xvr_b200.DRR(make_subject(16), 1020.0, 8, 2.0, renderer="trilinear")
+    reg = Registrar(drr, scales="4,2", n_itrs="50,20", provenance={"volume": "ct.nii.gz", "labels": [1, 2]})
+    info = {"params": [[0.0] * 6, [0.1] * 6], "nccs": [0.5, 0.6], "times": [0.0, 0.01], "alphas": [[1e-2, 1.0]] * 2}
+    traj = reg.trajectory(info)
+    assert list(traj.columns if hasattr(traj, "columns") else traj) == list(Registrar.COLUMNS)
+    intr = dict(sdd=1020.0, height=8, width=8, delx=2.0, dely=2.0, x0=-1.5, y0=0.5)
+    eye = torch.eye(4)[None]
+    reg.save(tmp_path, torch.zeros(1, 1, 8, 8), None, None, "xray_0001", intr, eye, eye * 2,
+             dict(pf_to_af=None, runtime=0.01, trajectory=traj))
+    got = torch.load(tmp_path / "parameters.pt", weights_only=False)
+    assert set(got) == {"drr", "xray", "optimization", "init_pose", "final_pose", "pf_to_af", "runtime", "trajectory"}
+    assert set(got["drr"]) == {"volume", "mask", "labels", "orientation", "sdd", "height", "width", "delx", "dely",
+                               "x0", "y0", "reverse_x_axis", "renderer", "read_kwargs", "drr_kwargs"}
+    assert set(got["xray"]) == {"filename", "crop", "subtract_background", "linearize", "reducefn"}
+    assert set(got["optimization"]) == {"equalize", "init_only", "scales", "n_itrs", "parameterization", "convention",
+                                        "lr_rot", "lr_xyz", "patience", "max_n_plateaus"}
+    assert got["drr"]["volume"].name == "ct.nii.gz" and got["drr"]["renderer"] == "trilinear"
+    assert got["optimization"]["scales"] == "4,2" and got["optimization"]["n_itrs"] == "50,20"
+    assert torch.equal(got["final_pose"], eye * 2) and got["drr"]["x0"] == -1.5
+    with pytest.raises(ValueError, match="ONE X-ray"):
+        reg.run(torch.zeros(2, 1, 8, 8), xvr_b200.RigidTransform(torch.eye(4).repeat(2, 1, 1)))
+
+
+def test_reference_private_correct_pose_signature():
+    """inference._correct_pose(pose, warp, volume, invert) is callable the way the reference calls it
+    (/root/reference/src/xvr/model/inference.py:42-48)."""
+    from xvr_b200 import inference
+
+    pose = xvr_b200.convert(torch.tensor([[0.1, 0.2, 0.3]]), torch.tensor([[1.0, 2.0, 3.0]]),
+                            parameterization="euler_angles", convention="ZXY")
+    assert inference._correct_pose(pose, None, None, False) is pose
+    shift = xvr_b200.convert(torch.tensor([[0.0, 0.1, 0.0]]), torch.tensor([[5.0, 0.0, 0.0]]),
+                             parameterization="euler_angles", convention="ZXY")
+    fwd = inference._correct_pose(pose, shift.matrix[0], None, False)
+    back = inference._correct_pose(fwd, shift.matrix[0], None, True)
+    assert torch.allclose(fwd.matrix, pose.compose(shift).matrix)
+    assert torch.allclose(back.matrix, pose.matrix, atol=1e-5)
+    with pytest.raises(NotImplementedError):
+        inference._correct_pose(pose, "warp.mat", "ct.nii.gz", False)
+
+
+def test_options_word_encoding():
+    """The per-call options word of include/xvr_b200.h, as the host composes it."""
+    from xvr_b200._lib import options, opts_word
+
+    assert opts_word() == 0
+    with options(ksplit=2, siddon_walk=False, volgrad="gather", siddon_tol="exact"):
+        assert opts_word() == (3 | 0x10 | 0x20 | (1 << 8))
+    assert opts_word() == 0
+    with pytest.raises(TypeError):
+        options(nonsense=1)
+    with pytest.raises(ValueError), options(ksplit=7):
+        pass
+    assert opts_word() == 0

@@ -1,0 +1,109 @@
+"""GPU parity of the pose parameterisations: every parameterisation of
+``convert`` against ``oracle.pose_from_params`` -- matrices and gradients -- through the one-launch kernels of
+csrc/pose.cu (and torch.linalg.eigh for rotation_10d), and a DRR rendered from each of them."""
+
+import pytest
+import torch
+
+import oracle
+import xvr_b200
+from xvr_b200.pose import N_ANGULAR_COMPONENTS, POSE_KERNEL_KINDS, RigidTransform
+
+pytestmark = pytest.mark.gpu
+
+CASES = [("euler_angles", "ZXY"), ("euler_angles", "XYZ"), ("euler_angles", "ZYZ"), ("axis_angle", None),
+         ("so3_log_map", None), ("se3_log_map", None), ("quaternion", None), ("rotation_6d", None),
+         ("quaternion_adjugate", None), ("rotation_10d", None)]
+
+
+def _random_params(parameterization, convention, B, device, seed=0):
+    """Parameters of random rigid motions, obtained by converting random Euler poses (so that every
+    parameterisation describes the same well-conditioned rotations), plus a perturbation off the constraint
+    manifold for the over-parameterised ones (unnormalised quaternions, non-orthogonal 6-D pairs)."""
+    g = torch.Generator().manual_seed(seed)
+    ang = (torch.rand(B, 3, generator=g) - 0.5) * torch.tensor([2.4, 1.2, 2.4])
+    xyz = (torch.rand(B, 3, generator=g) - 0.5) * 200 + torch.tensor([0.0, 800.0, 0.0])
+    pose = RigidTransform(oracle.pose_from_params(ang, xyz, "euler_angles", "ZXY"))
+    rot, t = pose.convert(parameterization, convention)
+    if parameterization in ("quaternion", "rotation_6d", "quaternion_adjugate"):
+        rot = rot * (1.0 + 0.3 * torch.rand(B, 1, generator=g)) + 0.02 * torch.randn(rot.shape, generator=g)
+    return rot.to(device).contiguous(), t.to(device).contiguous()
+
+
+@pytest.mark.parametrize("parameterization,convention", CASES)
+def test_convert_matches_oracle_matrices_and_gradients(cuda, parameterization, convention):
+    B = 37
+    rot, xyz = _random_params(parameterization, convention, B, cuda)
+    assert rot.shape[1] == N_ANGULAR_COMPONENTS[parameterization]
+    w = torch.randn(B, 4, 4, generator=torch.Generator().manual_seed(5)).to(cuda)
+    w[:, 3] = 0  # the constant row carries no gradient
+
+    r1, x1 = rot.clone().requires_grad_(), xyz.clone().requires_grad_()
+    n0 = xvr_b200._lib.lib().xvr_launch_count()
+    m1 = xvr_b200.convert(r1, x1, parameterization=parameterization, convention=convention).matrix
+    launched = xvr_b200._lib.lib().xvr_launch_count() - n0
+    assert launched == (1 if parameterization in POSE_KERNEL_KINDS else 0)  # the kernel really ran
+    (m1 * w).sum().backward()
+
+    # oracle in fp64 (the arbiter) and in fp32 (what the reference computes)
+    refs = {}
+    for dt in (torch.float64, torch.float32):
+        r2, x2 = rot.to(dt).requires_grad_(), xyz.to(dt).requires_grad_()
+        m2 = oracle.pose_from_params(r2, x2, parameterization, convention)
+        (m2 * w.to(dt)).sum().backward()
+        refs[dt] = (m2.detach(), r2.grad, x2.grad)
+    m64, gr64, gx64 = refs[torch.float64]
+    m32, gr32, gx32 = refs[torch.float32]
+
+    def err(a, b):
+        return ((a.double() - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+    # rotation_10d goes through an iterative eigen-solver on both sides: its fp32 noise floor is higher
+    bar = 2e-4 if parameterization == "rotation_10d" else 2e-6
+    gbar = 2e-3 if parameterization == "rotation_10d" else 2e-5
+    assert err(m1, m64) < bar, err(m1, m64)
+    # the kernel is no further from the fp64 arbiter than the reference's own fp32 arithmetic (x4 + floor)
+    assert err(r1.grad, gr64) < max(gbar, 4 * err(gr32, gr64)), (err(r1.grad, gr64), err(gr32, gr64))
+    assert err(x1.grad, gx64) < max(gbar, 4 * err(gx32, gx64)), (err(x1.grad, gx64), err(gx32, gx64))
+
+
+def test_degrees_and_empty_batches(cuda):
+    rot = torch.tensor([[30.0, -20.0, 10.0]], device=cuda, requires_grad=True)
+    xyz = torch.tensor([[5.0, 800.0, -3.0]], device=cuda)
+    m = xvr_b200.convert(rot, xyz, parameterization="euler_angles", convention="ZXY", degrees=True).matrix
+    ref = oracle.pose_from_params(rot.detach(), xyz, "euler_angles", "ZXY", degrees=True)
+    assert torch.allclose(m, ref, atol=1e-5)
+    m.sum().backward()
+    r2 = rot.detach().clone().requires_grad_()
+    oracle.pose_from_params(r2, xyz, "euler_angles", "ZXY", degrees=True).sum().backward()
+    assert torch.allclose(rot.grad, r2.grad, rtol=1e-4, atol=1e-4)
+    empty = xvr_b200.convert(torch.zeros(0, 10, device=cuda), torch.zeros(0, 3, device=cuda),
+                             parameterization="quaternion_adjugate")
+    assert tuple(empty.matrix.shape) == (0, 4, 4)
+
+
+@pytest.mark.parametrize("parameterization,convention", CASES)
+def test_drr_from_every_parameterisation_matches_oracle(cuda, parameterization, convention):
+    """DRR.forward(rot, xyz, parameterization=...) -- the call Registration.forward makes
+    (/root/reference/src/xvr/registrar/base.py:249) -- renders the oracle's image and back-propagates the oracle's
+    gradient for every parameterisation (pose kernel -> fused renderer -> Jacobian epilogue -> pose kernel backward)."""
+    from tests._scene import make_drr, rel_l2
+
+    drr = make_drr(64, 32)
+    B = 3
+    rot, xyz = _random_params(parameterization, convention, B, cuda, seed=3)
+    w = torch.rand(B, 1, 32, 32, generator=torch.Generator().manual_seed(1)).to(cuda)
+    r1, x1 = rot.clone().requires_grad_(), xyz.clone().requires_grad_()
+    img = drr(r1, x1, parameterization=parameterization, convention=convention)
+    (img * w).sum().backward()
+
+    r2, x2 = rot.clone().requires_grad_(), xyz.clone().requires_grad_()
+    pose = oracle.pose_from_params(r2, x2, parameterization, convention)
+    d = drr.detector
+    ref = oracle.drr_forward(drr.density, drr._affine_inverse[None], pose, reorient=d._reorient, height=d.height,
+                             width=d.width, delx=d.delx, dely=d.dely, x0=d.x0, y0=d.y0, sdd=d.sdd,
+                             reverse_x_axis=d.reverse_x_axis)
+    (ref * w).sum().backward()
+    assert rel_l2(img.detach(), ref.detach()) < 1e-4
+    gbar = 5e-3 if parameterization == "rotation_10d" else 2e-3
+    assert rel_l2(r1.grad, r2.grad) < gbar and rel_l2(x1.grad, x2.grad) < gbar

@@ -5,7 +5,7 @@ import torch
 
 import xvr_b200
 from tests._scene import make_drr, oracle_render, pose_params, rel_l2
-from xvr_b200._lib import call, ptr, stream
+from xvr_b200._lib import call, options, opts_word, ptr, stream
 
 pytestmark = pytest.mark.gpu
 
@@ -31,7 +31,7 @@ def _trace(vol, source, target, shift, max_seg):
     seg = torch.zeros(B, N, max_seg, device=vol.device)
     cnt = torch.zeros(B, N, dtype=torch.int32, device=vol.device)
     call("xvr_siddon_trace", ptr(vol), *vol.shape, ptr(source), ptr(target), B, N, shift, 1e-8, max_seg, ptr(idx),
-         ptr(seg), ptr(cnt), stream())
+         ptr(seg), ptr(cnt), opts_word(), stream())
     return idx, seg, cnt
 
 
@@ -126,12 +126,8 @@ def test_hoisted_reciprocal_division_is_ieee_exact(cuda):
 def _trace_digest(drr, source, target, shift, scale, max_seg):
     """Per-ray digests of the traversal (segment count, sum of voxel indices, sum of idx * position) computed with
     the fast-index certificate tolerance scaled by `scale`."""
-    call("xvr_set_siddon_index_tol_scale", float(scale))
-    try:
-        idx, seg, cnt = _trace(drr.density, source, target, shift, max_seg)
-    finally:
-        call("xvr_set_siddon_index_tol_scale", 1.0)
-    return idx, seg, cnt
+    with options(siddon_tol=scale, siddon_walk=False):
+        return _trace(drr.density, source, target, shift, max_seg)
 
 
 @pytest.mark.parametrize("n,h,b,shift,stretch", [(256, 160, 6, 0.5, 1.0), (200, 128, 4, 0.0, 1.0),
@@ -147,10 +143,73 @@ def test_fast_index_equals_exact_index(cuda, n, h, b, shift, stretch):
         centre = target.mean(1, keepdim=True)
         source = (centre + stretch * (source - centre)).contiguous()
     M = 3 * n + 8
-    idx_f, seg_f, cnt_f = _trace_digest(drr, source, target, shift, 1.0, M)
-    idx_e, seg_e, cnt_e = _trace_digest(drr, source, target, shift, 1e30, M)
+    idx_f, seg_f, cnt_f = _trace_digest(drr, source, target, shift, "production", M)
+    idx_e, seg_e, cnt_e = _trace_digest(drr, source, target, shift, "exact", M)
     assert cnt_f.max().item() <= M
     assert torch.equal(cnt_f, cnt_e)
     assert torch.equal(seg_f, seg_e)
     assert torch.equal(idx_f, idx_e)
     assert cnt_f.sum().item() > 2_000_000
+
+
+# ------------------------------------------------------------------------------------------ integer walk (default)
+@pytest.mark.parametrize("walk", [True, False], ids=["walk", "checked"])
+@pytest.mark.parametrize("n,h,b,shift", [(64, 48, 4, 0.5), (40, 33, 3, 0.0), (256, 128, 2, 0.5)])
+def test_walk_and_checked_traversals_are_bit_exact(cuda, walk, n, h, b, shift):
+    """Both ways of obtaining a segment's voxel index -- the integer walk with its one-compare certificate (default)
+    and the certified three-axis evaluation (XVR_OPT_SIDDON_CHECKED) -- against the oracle's reconstruction of the
+    reference's indices."""
+    import oracle
+    from tests._scene import make_drr, pose_params
+
+    drr = make_drr(n, h, renderer="siddon", voxel_shift=shift)
+    rot, xyz = pose_params(b, seed=11)
+    source, target, _ = _rays(drr, rot, xyz)
+    ref_idx, ref_seg = oracle.siddon_segments(tuple(drr.density.shape), source, target, voxel_shift=shift)
+    M = ref_idx.shape[-1]
+    with options(siddon_walk=walk):
+        idx, seg, cnt = _trace(drr.density, source, target, shift, M + 8)
+    ref_valid = torch.diff(oracle.siddon_alphas(source, target, tuple(drr.density.shape), shift, 1e-8), dim=-1)
+    ref_cnt = (~ref_valid.isnan()).sum(-1).to(torch.int32)
+    assert torch.equal(cnt, ref_cnt)
+    live = torch.arange(M, device=cuda)[None, None] < ref_cnt[..., None]
+    pos = live & (ref_seg > 0)  # ties between axes may be emitted in either order: zero-length segments are exempt
+    assert torch.equal(seg[..., :M][live], ref_seg[live])
+    assert torch.equal(idx[..., :M][pos].long(), ref_idx[pos])
+
+
+def test_walk_renders_bit_identical_images_and_gradients(cuda):
+    """Fused Siddon DRR (rays generated in-kernel) with and without the integer walk: same images, same gradients."""
+    from tests._scene import make_drr, pose_params
+
+    drr = make_drr(128, 64, renderer="siddon")
+    rot, xyz = pose_params(3, seed=3)
+    outs = []
+    for walk in (False, True):
+        with options(siddon_walk=walk):
+            r, x = rot.clone().requires_grad_(), xyz.clone().requires_grad_()
+            img = drr(xvr_b200.convert(r, x, parameterization="euler_angles", convention="ZXY"))
+            img.sum().backward()
+            outs.append((img.detach().clone(), r.grad.clone(), x.grad.clone()))
+    for u, v in zip(*outs):
+        assert torch.equal(u, v)
+
+
+def test_fused_siddon_drr_matches_materialised_rays(cuda, monkeypatch):
+    """xvr_siddon_drr_fwd (in-kernel ray generation, no (B,N,3) tensors) against the materialised-ray entry the
+    reference's Trainer.render_samples sequence uses: images to 1e-5 (the composed camera -> voxel matrix rounds
+    differently from the two-step transform), pose gradients to 1e-3."""
+    from tests._scene import make_drr, pose_params, rel_l2
+
+    drr = make_drr(96, 64, renderer="siddon", width=48)
+    rot, xyz = pose_params(3, seed=21)
+    outs = []
+    for fused in ("1", "0"):
+        monkeypatch.setenv("XVR_B200_FUSED", fused)
+        r, x = rot.clone().requires_grad_(), xyz.clone().requires_grad_()
+        img = drr(xvr_b200.convert(r, x, parameterization="euler_angles", convention="ZXY"))
+        w = torch.rand(img.shape, generator=torch.Generator().manual_seed(2)).to(img.device)
+        (img * w).sum().backward()
+        outs.append((img.detach().clone(), r.grad.clone(), x.grad.clone()))
+    assert rel_l2(outs[0][0], outs[1][0]) < 1e-5
+    assert rel_l2(outs[0][1], outs[1][1]) < 1e-3 and rel_l2(outs[0][2], outs[1][2]) < 1e-3

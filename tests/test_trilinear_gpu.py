@@ -221,20 +221,17 @@ def test_pose_gradients_smooth_volume_tight(cuda, monkeypatch, fused):
 
 @pytest.fixture
 def volgrad_version(request):
-    from xvr_b200._lib import call
+    from xvr_b200._lib import options
 
-    call("xvr_set_volgrad_version", request.param)
-    yield request.param
-    call("xvr_set_volgrad_version", 2)  # the library default
+    with options(volgrad=request.param):
+        yield request.param
 
 
-# version 1 (the voxel-centric gather kept as a cross-check) was last changed after its last GPU run: its turn at
-# these cases is in tests/test_zzz_unrun_gpu.py
-@pytest.mark.parametrize("volgrad_version", [2], indirect=True)
+@pytest.mark.parametrize("volgrad_version", ["brick", "gather"], indirect=True)
 @pytest.mark.parametrize("n,h,b", [(24, 16, 3), (40, 33, 2), (50, 64, 2)])
 def test_volume_gradient_matches_oracle_and_is_deterministic(cuda, n, h, b, volgrad_version):
-    """dL/dvolume (atomics-free brick-local scatter) vs autograd through
-    grid_sample's atomicAdd scatter."""
+    """dL/dvolume (atomics-free: brick-local scatter, and the voxel-centric gather kept as an independent
+    cross-check) vs autograd through grid_sample's atomicAdd scatter."""
     import oracle
 
     drr = make_drr(n, h)
@@ -296,20 +293,17 @@ def test_texture_tracks_volume_updates(cuda):
 
 def test_sample_slicing_across_lanes_matches_one_lane_per_ray(cuda):
     """Small batches split each ray's samples over 2/4/8 lanes; images and Jacobians agree to summation order."""
-    from xvr_b200._lib import lib
+    from xvr_b200._lib import options
 
     drr = make_drr(64, 40, width=24)
     rot, xyz = pose_params(2, seed=15)
     res = []
-    try:
-        for ks in (0, 1, 2, 3, -1):
-            assert lib().xvr_set_ksplit(ks) == 0
+    for ks in (0, 1, 2, 3, None):
+        with options(ksplit=ks):
             r, x = rot.clone().requires_grad_(), xyz.clone().requires_grad_()
             img = _render(drr, r, x)
             img.sum().backward()
             res.append((img.detach(), r.grad, x.grad))
-    finally:
-        lib().xvr_set_ksplit(-1)
     for img, gr, gx in res[1:]:
         assert rel_l2(img, res[0][0]) < 1e-6
         assert rel_l2(gr, res[0][1]) < 1e-4 and rel_l2(gx, res[0][2]) < 1e-4
@@ -317,18 +311,15 @@ def test_sample_slicing_across_lanes_matches_one_lane_per_ray(cuda):
 
 
 def test_tile_shapes_give_identical_images(cuda, monkeypatch):
-    from xvr_b200._lib import lib
+    from xvr_b200._lib import options
 
     drr = make_drr(64, 64)
     rot, xyz = pose_params(2, seed=8)
     imgs = []
-    lib().xvr_set_ksplit(0)  # one lane per ray: the per-ray summation order is then independent of the tile shape
-    try:
+    with options(ksplit=0):  # one lane per ray: the per-ray summation order is then independent of the tile shape
         for tile in ("3,4", "5,5", "0,0", "2,3", "5,8"):
             monkeypatch.setenv("XVR_B200_TILE", tile)
             imgs.append(_render(drr, rot, xyz))
-    finally:
-        lib().xvr_set_ksplit(-1)
     for im in imgs[1:]:
         assert torch.equal(im, imgs[0])
 

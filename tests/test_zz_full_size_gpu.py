@@ -224,7 +224,7 @@ def test_config5_traversal_is_bit_exact_on_a_ray_sample(config5):
     seg = torch.zeros(B, N, M + 8, device=target.device)
     cnt = torch.zeros(B, N, dtype=torch.int32, device=target.device)
     call("xvr_siddon_trace", ptr(drr.density), *shape, ptr(source), ptr(target), B, N, 0.5, 1e-8, M + 8, ptr(idx),
-         ptr(seg), ptr(cnt), stream())
+         ptr(seg), ptr(cnt), 0, stream())
     assert torch.equal(cnt, ref_cnt.to(torch.int32))
     live = torch.arange(M, device=target.device)[None, None] < ref_cnt[..., None]
     assert live.sum() > 1_000_000
@@ -264,13 +264,13 @@ def test_config5_is_bit_reproducible(config5):
 
 
 # ------------------------------------------------------------------------------------------ dL/dvolume, edge geometry
-# The library default (brick-local scatter).  The gather kernel (version 1) was last changed after its last GPU run;
-# its turn at these cases is in tests/test_zzz_unrun_gpu.py.
-@pytest.fixture(params=[2], ids=["brick"])
+# Both formulations: the library default (brick-local scatter) and the voxel-centric gather (cross-check).
+@pytest.fixture(params=["brick", "gather"])
 def volgrad_version(request):
-    call("xvr_set_volgrad_version", request.param)
-    yield request.param
-    call("xvr_set_volgrad_version", 2)
+    from xvr_b200._lib import options
+
+    with options(volgrad=request.param):
+        yield request.param
 
 
 def _volume_gradient_vs_oracle(drr, rot, xyz):
@@ -316,10 +316,9 @@ EDGE_ROT = [[0.0, 0.0, 0.0], [0.0, 0.0, 0.0], [1.2, 0.3, 0.0], [0.0, 0.0, 0.0], 
 EDGE_XYZ = [[0.0, 800.0, 0.0], [400.0, 800.0, 0.0], [0.0, 300.0, 0.0], [10.0, 60.0, -5.0], [128.0, 500.0, 127.5]]
 
 
-def test_volume_gradient_edge_poses(cuda):
+def test_volume_gradient_edge_poses(cuda, volgrad_version):
     """Rays missing the volume, grazing it, the source inside the volume (bricks behind the source), axis-aligned
-    rays -- the poses of test_forward_edge_poses -- through the library default (brick-local scatter).  The gather
-    kernel's turn at these poses is in tests/test_zzz_unrun_gpu.py."""
+    rays -- the poses of test_forward_edge_poses -- through both formulations."""
     from tests._scene import make_drr
 
     drr = make_drr(64, 32)

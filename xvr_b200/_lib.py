@@ -23,13 +23,13 @@ _SIGNATURES = {
     "xvr_volume_destroy": ([P], c_int),
     "xvr_trilinear_rays_fwd": (
         [P, P, c_int, c_int, c_int, P, c_int, P, P, P, c_int, c_int, c_int, c_int, c_float, c_int, c_int, c_int,
-         c_int, P, P, P], c_int),
+         c_int, P, P, c_int, P], c_int),
     "xvr_trilinear_rays_bwd": (
         [P, P, c_int, c_int, c_int, P, c_int, P, P, P, c_int, c_int, c_int, c_int, c_float, c_int, c_int, c_int,
          c_int, P, P, P, P, P, P], c_int),
     "xvr_trilinear_drr_fwd": (
         [P, P, c_int, c_int, c_int, P, P, ctypes.POINTER(c_float), c_int, c_int, c_int, c_int, c_int, c_float, c_int,
-         c_int, P, P, P], c_int),
+         c_int, P, P, c_int, P], c_int),
     "xvr_trilinear_drr_fwd_staged": (
         [P, c_int, c_int, c_int, P, P, ctypes.POINTER(c_float), c_int, c_int, c_int, c_int, c_int, c_float, c_int, P, P,
          P, P], c_int),
@@ -37,11 +37,7 @@ _SIGNATURES = {
     "xvr_drr_jac_bwd_slices": ([c_int, c_int], c_int),
     "xvr_trilinear_drr_bwd_volume": (
         [P, P, P, ctypes.POINTER(c_float), c_int, c_int, c_int, c_int, c_int, c_float, P, c_int, c_int, c_int, P, P,
-         c_int, P], c_int),
-    "xvr_set_ksplit": ([c_int], c_int),
-    "xvr_set_volgrad_version": ([c_int], c_int),
-    "xvr_set_siddon_index_tol_scale": ([c_float], c_int),
-    "xvr_set_siddon_walk": ([c_int], c_int),
+         c_int, c_int, P], c_int),
     "xvr_rays_jac_bwd": ([P, P, c_int, c_int, P, P, P, P, P], c_int),
     "xvr_ncc_fwd": ([P, P, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_int, P, P, P, P, P], c_int),
     "xvr_ncc_bwd": ([P, P, P, c_int, P, c_int, c_int, c_int, c_int, c_int, c_float, c_int, P, P], c_int),
@@ -57,17 +53,72 @@ _SIGNATURES = {
                               ctypes.POINTER(c_float), P, P, P], c_int),
     "xvr_euler_camera_bwd": ([P, P, c_int, ctypes.POINTER(c_int), c_int, ctypes.POINTER(c_float),
                               ctypes.POINTER(c_float), P, P, P, P], c_int),
+    "xvr_pose_fwd": ([P, P, c_int, c_int, c_int, ctypes.POINTER(c_int), c_int, c_float, ctypes.POINTER(c_float),
+                      ctypes.POINTER(c_float), P, P, P, P], c_int),
+    "xvr_pose_bwd": ([P, P, c_int, c_int, c_int, ctypes.POINTER(c_int), c_int, c_float, ctypes.POINTER(c_float),
+                      ctypes.POINTER(c_float), P, P, P, P, P], c_int),
     "xvr_reg_update": ([P, P, P, P, c_int, P, P, P, P, P, P, P, P, c_int, ctypes.POINTER(ctypes.c_double), P], c_int),
     "xvr_siddon_rays_fwd": (
         [P, c_int, c_int, c_int, P, c_int, P, P, P, c_int, c_int, c_float, c_float, c_int, c_int, c_int, c_int, P, P,
-         P], c_int),
+         c_int, P], c_int),
+    "xvr_siddon_drr_fwd": (
+        [P, c_int, c_int, c_int, P, P, ctypes.POINTER(c_float), c_int, c_int, c_int, c_float, c_float, c_int, c_int, P,
+         P, c_int, P], c_int),
     "xvr_siddon_rays_bwd": (
         [P, c_int, c_int, c_int, P, c_int, P, P, P, c_int, c_int, c_float, c_float, c_int, c_int, c_int, c_int, P, P,
-         P, P, P, P], c_int),
+         P, P, P, c_int, P], c_int),
     "xvr_selftest_division": ([c_int, c_int, ctypes.c_uint, P, P], c_int),
     "xvr_siddon_trace": (
-        [P, c_int, c_int, c_int, P, P, c_int, c_int, c_float, c_float, c_int, P, P, P, P], c_int),
+        [P, c_int, c_int, c_int, P, P, c_int, c_int, c_float, c_float, c_int, P, P, P, c_int, P], c_int),
 }
+
+# ---- per-call kernel options (include/xvr_b200.h XVR_OPT_*).  The library itself keeps no mutable state: the
+# variant travels with every call.  This host-side holder only supplies the word; tests and tuning scripts change it
+# with `with options(siddon_walk=False): ...`.
+_OPTION_DEFAULTS = {"ksplit": None, "siddon_walk": True, "volgrad": "brick", "siddon_tol": "production"}
+_options = dict(_OPTION_DEFAULTS)
+_TOL_CODES = {"production": 0, "exact": 1, 0.5: 2, 0.25: 3, 0.125: 4}
+
+
+def opts_word():
+    w = 0
+    if _options["ksplit"] is not None:
+        if _options["ksplit"] not in (0, 1, 2, 3):
+            raise ValueError("ksplit must be None (automatic) or 0..3 (log2 of the lanes per ray)")
+        w |= _options["ksplit"] + 1
+    if not _options["siddon_walk"]:
+        w |= 0x10
+    if _options["volgrad"] == "gather":
+        w |= 0x20
+    elif _options["volgrad"] != "brick":
+        raise ValueError("volgrad must be 'brick' or 'gather'")
+    w |= _TOL_CODES[_options["siddon_tol"]] << 8
+    return w
+
+
+class options:
+    """Context manager: ``with options(siddon_walk=False, volgrad="gather"): ...``"""
+
+    def __init__(self, **kw):
+        unknown = set(kw) - set(_OPTION_DEFAULTS)
+        if unknown:
+            raise TypeError(f"unknown kernel option(s): {sorted(unknown)}")
+        self.kw = kw
+
+    def __enter__(self):
+        self.saved = dict(_options)
+        _options.update(self.kw)
+        try:
+            opts_word()  # validate now
+        except Exception:
+            self.__exit__()
+            raise
+        return self
+
+    def __exit__(self, *exc):
+        _options.clear()
+        _options.update(self.saved)
+        return False
 
 
 class XvrB200Error(RuntimeError):

@@ -28,7 +28,7 @@ int check_launch(const char* what) {
 
 extern "C" const char* xvr_last_error(void) { return xvr::g_last_error; }
 
-extern "C" int xvr_abi_version(void) { return 1; }
+extern "C" int xvr_abi_version(void) { return 2; }
 
 // Number of kernels this library has launched since load (bench.py's gpu_launches evidence).
 extern "C" long long xvr_launch_count(void) { return xvr::g_launches; }

@@ -11,6 +11,13 @@
 #define XVR_ERR_INVALID -1
 #define XVR_ERR_CUDA -2
 
+// Per-call options word `opts` of the entry points that have variants (include/xvr_b200.h XVR_OPT_*; 0 = default).
+#define XVR_OPT_KSPLIT_MASK 0x7        // 0: automatic, 1..4: 1/2/4/8 lanes share one ray (trilinear forward)
+#define XVR_OPT_SIDDON_CHECKED 0x10    // Siddon: every voxel index through the certified evaluation, no integer walk
+#define XVR_OPT_VOLGRAD_GATHER 0x20    // dL/dvolume: voxel-centric gather instead of the brick-local scatter
+#define XVR_OPT_SIDDON_TOL_SHIFT 8     // bits 8..11, test hook: certificate tolerance 0: x1, 1: always exact, 2..4: x1/2, 1/4, 1/8
+#define XVR_OPT_KNOWN 0xF37
+
 namespace xvr {
 
 void set_last_error(const char* msg);

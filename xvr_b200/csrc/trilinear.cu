@@ -388,8 +388,6 @@ __global__ void drr_jac_bwd_finish_kernel(const float* __restrict__ partial, int
   gG[i] = v;
 }
 
-static int g_ksplit = -1;  // -1: automatic
-
 static int fill_geom(DetectorGeom& g, const float* cam2vox, const float* cam2world, const float* det9, int W) {
   if (!cam2vox || !cam2world || !det9 || W <= 0) {
     set_last_error("xvr_drr: null geometry argument");
@@ -445,9 +443,10 @@ static int fill_common(TrilinearParams& p, const float* volume, const void* volt
                        const uint8_t* labels,
                        int C, const float* source, const float* target, const float* raylen, int B, int N,
                        int n_points, int step_mode, float eps, int det_h, int det_w, int lane_w_log2,
-                       int cta_w_log2, bool allow_ksplit = true) {
+                       int cta_w_log2, int opts, bool allow_ksplit = true) {
   if (!volume || ((!source || !target || !raylen) && !p.fused) || B <= 0 || N <= 0 || D0 < 2 || D1 < 2 || D2 < 2 ||
-      n_points < 2 || step_mode < 0 || step_mode > 2 || C < 1 || (labels && C > 255) || (!labels && C != 1)) {
+      n_points < 2 || step_mode < 0 || step_mode > 2 || C < 1 || (labels && C > 255) || (!labels && C != 1) ||
+      (opts & ~XVR_OPT_KNOWN) || (opts & XVR_OPT_KSPLIT_MASK) > 4) {
     set_last_error("xvr_trilinear: invalid argument");
     return XVR_ERR_INVALID;
   }
@@ -485,8 +484,8 @@ static int fill_common(TrilinearParams& p, const float* volume, const void* volt
   // fewer lanes per ray on ties.  Launches of more than ~16 waves are left alone: their tail is < 6 %.
   int ks = 0;
   if (!labels && allow_ksplit) {
-    if (g_ksplit >= 0) {
-      ks = g_ksplit;
+    if (opts & XVR_OPT_KSPLIT_MASK) {
+      ks = (opts & XVR_OPT_KSPLIT_MASK) - 1;
     } else {
       const double wave = 148.0 * XVR_TRI_MIN_CTAS;
       double best = 1e30;
@@ -513,10 +512,11 @@ extern "C" int xvr_trilinear_rays_fwd(const float* volume, const void* voltex, i
                                       const uint8_t* labels, int C,
                                       const float* source, const float* target, const float* raylen, int B,
                                       int N, int n_points, int step_mode, float eps, int det_h, int det_w,
-                                      int lane_w_log2, int cta_w_log2, float* out, float* jac, void* stream) {
+                                      int lane_w_log2, int cta_w_log2, float* out, float* jac, int opts,
+                                      void* stream) {
   TrilinearParams p = {};
   int rc = fill_common(p, volume, voltex, D0, D1, D2, labels, C, source, target, raylen, B, N, n_points, step_mode, eps,
-                       det_h, det_w, lane_w_log2, cta_w_log2);
+                       det_h, det_w, lane_w_log2, cta_w_log2, opts);
   if (rc) return rc;
   if (!out) {
     set_last_error("xvr_trilinear_rays_fwd: out is null");
@@ -556,7 +556,7 @@ extern "C" int xvr_trilinear_rays_bwd(const float* volume, const void* voltex, i
                                       float* gtarget, float* graylen, float* workspace, void* stream) {
   TrilinearParams p = {};
   int rc = fill_common(p, volume, voltex, D0, D1, D2, labels, C, source, target, raylen, B, N, n_points, step_mode, eps,
-                       det_h, det_w, lane_w_log2, cta_w_log2, false);
+                       det_h, det_w, lane_w_log2, cta_w_log2, 0, false);
   if (rc) return rc;
   if (!gout || !gsource || !gtarget || !graylen || !workspace) {
     set_last_error("xvr_trilinear_rays_bwd: null gradient buffer");
@@ -614,13 +614,13 @@ extern "C" int xvr_rays_jac_bwd(const float* jac, const float* gout, int B, int 
 extern "C" int xvr_trilinear_drr_fwd(const float* volume, const void* voltex, int D0, int D1, int D2,
                                      const float* cam2vox, const float* cam2world, const float* det9, int B,
                                      int det_h, int det_w, int n_points, int step_mode, float eps, int lane_w_log2,
-                                     int cta_w_log2, float* out, float* jac, void* stream) {
+                                     int cta_w_log2, float* out, float* jac, int opts, void* stream) {
   TrilinearParams p = {};
   p.fused = true;
   int rc = fill_geom(p.geom, cam2vox, cam2world, det9, det_w);
   if (rc) return rc;
   rc = fill_common(p, volume, voltex, D0, D1, D2, nullptr, 1, nullptr, nullptr, nullptr, B, det_h * det_w, n_points,
-                   step_mode, eps, det_h, det_w, lane_w_log2, cta_w_log2);
+                   step_mode, eps, det_h, det_w, lane_w_log2, cta_w_log2, opts);
   if (rc) return rc;
   if (!out) {
     set_last_error("xvr_trilinear_drr_fwd: out is null");
@@ -678,15 +678,4 @@ extern "C" int xvr_drr_jac_bwd(const float* jac, const float* gout, const float*
   if (rc) return rc;
   drr_jac_bwd_finish_kernel<<<(B * 12 + 127) / 128, 128, 0, st>>>(workspace, B, S, gG);
   return check_launch("xvr_drr_jac_bwd/finish");
-}
-
-// Number of lanes that share one ray in the trilinear forward kernels, as log2 (0..3); -1 = automatic (grow until
-// the launch has about two waves of threads).  Tuning / test hook.
-extern "C" int xvr_set_ksplit(int ks_log2) {
-  if (ks_log2 < -1 || ks_log2 > 3) {
-    set_last_error("xvr_set_ksplit: expected -1 (auto) or 0..3");
-    return XVR_ERR_INVALID;
-  }
-  g_ksplit = ks_log2;
-  return XVR_OK;
 }

@@ -320,8 +320,6 @@ __global__ void __launch_bounds__(32) volume_grad_brick_kernel(const VolGradPara
   }
 }
 
-static int g_volgrad_version = 2;
-
 }  // namespace xvr
 
 using namespace xvr;
@@ -332,9 +330,9 @@ using namespace xvr;
 extern "C" int xvr_trilinear_drr_bwd_volume(const float* cam2vox, const float* vox2cam, const float* cam2world,
                                             const float* det9, int B, int det_h, int det_w, int n_points,
                                             int step_mode, float eps, const float* gout, int D0, int D1, int D2,
-                                            float* workspace, float* gvol, int accumulate, void* stream) {
+                                            float* workspace, float* gvol, int accumulate, int opts, void* stream) {
   if (!cam2vox || !vox2cam || !cam2world || !det9 || !gout || !workspace || !gvol || B <= 0 || det_h <= 0 ||
-      det_w <= 0 || n_points < 2 || D0 < 2 || D1 < 2 || D2 < 2) {
+      det_w <= 0 || n_points < 2 || D0 < 2 || D1 < 2 || D2 < 2 || (opts & ~XVR_OPT_KNOWN)) {
     set_last_error("xvr_trilinear_drr_bwd_volume: invalid argument");
     return XVR_ERR_INVALID;
   }
@@ -361,7 +359,7 @@ extern "C" int xvr_trilinear_drr_bwd_volume(const float* cam2vox, const float* v
   ray_info_kernel<<<(unsigned)((rays + 255) / 256), 256, 0, st>>>(p);
   int rc = check_launch("xvr_trilinear_drr_bwd_volume/info");
   if (rc) return rc;
-  if (g_volgrad_version == 2) {
+  if (!(opts & XVR_OPT_VOLGRAD_GATHER)) {
     const int64_t bricks = (int64_t)((D0 + VG_B - 1) / VG_B) * ((D1 + VG_B - 1) / VG_B) * ((D2 + VG_B - 1) / VG_B);
     volume_grad_brick_kernel<<<(unsigned)bricks, 32, 0, st>>>(p);
     return check_launch("xvr_trilinear_drr_bwd_volume/brick");
@@ -369,14 +367,4 @@ extern "C" int xvr_trilinear_drr_bwd_volume(const float* cam2vox, const float* v
   dim3 grid((D2 + 63) / 64, (D1 + 3) / 4, D0);
   volume_grad_kernel<<<grid, 256, 0, st>>>(p);
   return check_launch("xvr_trilinear_drr_bwd_volume");
-}
-
-// Selects the formulation: 2 = brick-local scatter (default), 1 = voxel-centric gather (kept as the cross-check).
-extern "C" int xvr_set_volgrad_version(int version) {
-  if (version != 1 && version != 2) {
-    set_last_error("xvr_set_volgrad_version: expected 1 or 2");
-    return XVR_ERR_INVALID;
-  }
-  g_volgrad_version = version;
-  return XVR_OK;
 }

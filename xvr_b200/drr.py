@@ -197,8 +197,8 @@ class DRR(torch.nn.Module):
             raise RuntimeError("drr.density was unloaded; call drr.renderer(volume, ...) directly "
                                "(as xvr's Trainer.render_samples does) or restore it")
         mask = getattr(self, "mask", None) if mask_to_channels else None
-        fused = (mask is None and calibration is None and isinstance(self.renderer, Trilinear) and self.reshape
-                 and os.environ.get("XVR_B200_FUSED", "1") == "1")
+        fused = (mask is None and calibration is None and isinstance(self.renderer, (Trilinear, Siddon))
+                 and self.reshape and os.environ.get("XVR_B200_FUSED", "1") == "1")
         degrees = kwargs.pop("degrees", False)
         if (fused and parameterization == "euler_angles" and len(args) == 2 and args[0].is_cuda and args[0].dim() == 2
                 and conv.COMPOSE_APPLIES_SELF_FIRST and os.environ.get("XVR_B200_FUSED_POSE", "1") == "1"):
@@ -210,6 +210,16 @@ class DRR(torch.nn.Module):
                                                     affinv16)
             img = self.renderer.render_drr(self.density, cam2vox, cam2world, self.detector, **kwargs)
             return self.reshape_transform(img, batch_size=rot.shape[0])
+        if (fused and parameterization is not None and len(args) == 2 and conv.COMPOSE_APPLIES_SELF_FIRST):
+            from .pose import POSE_KERNEL_KINDS, _kernel_eligible, _PoseKernel  # noqa: PLC0415
+
+            if _kernel_eligible(args[0], args[1], parameterization):
+                # any closed-form parameterisation straight to camera matrices (one launch), then the fused renderer
+                rot, xyz = args
+                cam2vox, cam2world = _PoseKernel.apply(rot, xyz, POSE_KERNEL_KINDS[parameterization], convention,
+                                                       degrees, self._host_matrices())
+                img = self.renderer.render_drr(self.density, cam2vox, cam2world, self.detector, **kwargs)
+                return self.reshape_transform(img, batch_size=rot.shape[0])
         if parameterization is None:
             (pose,) = args
         else:

@@ -95,6 +95,19 @@ def construct_antipode(pose):
     return convert(rot * flip + turn, xyz, parameterization="euler_angles", convention="ZXY")
 
 
-# the reference's private names, for scripts that import them
-_correct_pose = correct_pose
+def _correct_pose(pose, warp, volume=None, invert=False):
+    """The reference's private helper with its signature (inference.py:42-48): ``warp`` is ``None`` (no-op) or --
+    here -- the SE(3) transform itself (RigidTransform / (4,4) matrix), inverted first when ``invert``.  The
+    reference obtains that matrix from an ANTs warp *file* and the CT (``get_4x4(warp, volume, invert)``): file IO
+    through antspyx, out of scope, so a path raises instead of being silently ignored."""
+    if warp is None:
+        return pose
+    if isinstance(warp, (str, bytes)) or hasattr(warp, "__fspath__"):
+        raise NotImplementedError("reading an ANTs warp file needs antspyx (not part of the hot path); pass the 4x4 "
+                                  "transform it encodes instead")
+    frame = warp if isinstance(warp, RigidTransform) else RigidTransform(torch.as_tensor(warp, dtype=torch.float32))
+    return correct_pose(pose, frame.inverse() if invert else frame)
+
+
+# the reference's other private name, for scripts that import it
 _construct_antipode = construct_antipode

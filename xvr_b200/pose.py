@@ -6,9 +6,14 @@ Interface pinned by the xvr call sites: ``convert(rot, xyz, parameterization=, c
 ``__matmul__`` and ``__call__(points)`` (model/trainer.py:193,204,270,289; model/loss.py:45-49;
 registrar/base.py:168,201,264; metrics/evaluator.py:29) and ``make_matrix``.
 
-These are O(B) operations on 4x4 matrices -- not the bandwidth path -- and stay in PyTorch so that autograd
-carries dL/dG (the 3x4 camera->voxel gradient produced by the CUDA renderer) back to the pose parameters.
+These are O(B) operations on 4x4 matrices -- not the bandwidth path.  On CUDA tensors ``convert`` is ONE launch
+each way (csrc/pose.cu: forward per pose, backward per (pose, parameter) by forward-mode differentiation) for every
+parameterisation with a closed form; the tensor-op formulation below is the specification those kernels are tested
+against (and what CPU tensors and ``rotation_10d`` run).
 """
+
+import ctypes
+import os
 
 import torch
 
@@ -228,11 +233,75 @@ def _rotation(rot, xyz, parameterization, convention, degrees):
     raise ValueError(f"Unknown parameterization {parameterization!r}; choose from {list(N_ANGULAR_COMPONENTS)}")
 
 
+# parameterisations of csrc/pose.cu (enum PoseKind)
+POSE_KERNEL_KINDS = {"euler_angles": 0, "axis_angle": 1, "so3_log_map": 2, "se3_log_map": 3, "quaternion": 4,
+                     "rotation_6d": 5, "quaternion_adjugate": 6}
+
+
+def _euler_axes(convention):
+    if convention is None or len(convention) != 3 or any(c not in "XYZ" for c in convention):
+        raise ValueError(f"Invalid Euler convention {convention!r}")
+    return (ctypes.c_int * 3)(*("XYZ".index(c) for c in convention))
+
+
+class _PoseKernel(torch.autograd.Function):
+    """(rot (B,n), xyz (B,3)) -> pose (B,4,4) [and, with camera constants, cam2vox / cam2world (B,3,4)] through
+    xvr_pose_fwd / xvr_pose_bwd: one launch each way."""
+
+    @staticmethod
+    def forward(ctx, rot, xyz, kind, convention, degrees, camera):
+        from ._lib import call, cuda_f32, ptr, stream  # noqa: PLC0415
+
+        rot, xyz = cuda_f32(rot, "rotation"), cuda_f32(xyz, "translation")
+        B, n_rot = rot.shape
+        axes = _euler_axes(convention) if kind == 0 else None
+        scale = torch.pi / 180.0 if (degrees and kind == 0) else 1.0
+        consts = (B, kind, n_rot, axes, int(conv.CONVERT_TRANSLATION_IN_ROTATED_FRAME), float(scale))
+        ctx.save_for_backward(rot, xyz)
+        if camera is None:
+            pose = torch.empty(B, 4, 4, device=rot.device, dtype=torch.float32)
+            ctx.consts = (*consts, None, None)
+            if B > 0:
+                call("xvr_pose_fwd", ptr(rot), ptr(xyz), *ctx.consts, ptr(pose), None, None, stream())
+            return pose
+        reorient16, affinv16 = camera
+        ctx.consts = (*consts, (ctypes.c_float * 16)(*reorient16), (ctypes.c_float * 16)(*affinv16))
+        cam2world = torch.empty(B, 3, 4, device=rot.device, dtype=torch.float32)
+        cam2vox = torch.empty(B, 3, 4, device=rot.device, dtype=torch.float32)
+        if B > 0:
+            call("xvr_pose_fwd", ptr(rot), ptr(xyz), *ctx.consts, None, ptr(cam2world), ptr(cam2vox), stream())
+        ctx.mark_non_differentiable(cam2world)  # only feeds the ray length, which a rigid motion leaves unchanged
+        return cam2vox, cam2world
+
+    @staticmethod
+    def backward(ctx, g, *_unused):
+        from ._lib import call, cuda_f32, ptr, stream  # noqa: PLC0415
+
+        rot, xyz = ctx.saved_tensors
+        grot, gxyz = torch.empty_like(rot), torch.empty_like(xyz)
+        if rot.shape[0] > 0:
+            g = cuda_f32(g, "grad")
+            camera = ctx.consts[-1] is not None
+            call("xvr_pose_bwd", ptr(rot), ptr(xyz), *ctx.consts, None if camera else ptr(g), ptr(g) if camera else None,
+                 ptr(grot), ptr(gxyz), stream())
+        return grot, gxyz, None, None, None, None
+
+
+def _kernel_eligible(rot, xyz, parameterization):
+    return (parameterization in POSE_KERNEL_KINDS and torch.is_tensor(rot) and rot.is_cuda and xyz.is_cuda
+            and rot.dim() == 2 and xyz.dim() == 2 and rot.shape[0] == xyz.shape[0] and xyz.shape[1] == 3
+            and rot.shape[1] == N_ANGULAR_COMPONENTS[parameterization] and rot.dtype == torch.float32
+            and xyz.dtype == torch.float32 and os.environ.get("XVR_B200_FUSED_POSE", "1") == "1")
+
+
 def convert(*args, parameterization, convention=None, degrees=False):
     """``convert(rot, xyz, parameterization=..., convention=..., degrees=...) -> RigidTransform``."""
     if len(args) != 2:
         raise TypeError("convert(rot, xyz, parameterization=..., convention=...)")
     rot, xyz = args
+    if _kernel_eligible(rot, xyz, parameterization):
+        return RigidTransform(_PoseKernel.apply(rot, xyz, POSE_KERNEL_KINDS[parameterization], convention, degrees,
+                                                None))
     R, t = _rotation(rot, xyz, parameterization, convention, degrees)
     if conv.CONVERT_TRANSLATION_IN_ROTATED_FRAME and parameterization != "se3_log_map":
         t = (R @ t[..., None])[..., 0]

@@ -120,8 +120,12 @@ class Registrar:
     def __init__(self, drr, scales="8", n_itrs="500", parameterization="euler_angles", convention="ZXY", lr_rot=1e-2,
                  lr_xyz=1e0, patience=10, threshold=1e-4, max_n_plateaus=3, crop=0, equalize=False, mncc_patch_size=9,
                  gncc_patch_size=11, sigma=0.0, beta=0.5, use_cuda_graph=True, poll_every=16, fused_update=True,
-                 fused_similarity=False):
+                 fused_similarity=False, provenance=None, saveimg=False):
         self.drr = drr
+        # what the reference's registrars know from their constructor arguments and `save` writes into
+        # parameters.pt (base.py:355-394): volume / mask paths, labels, orientation, reverse_x_axis, renderer, ...
+        self.provenance = dict(provenance or {})
+        self.saveimg = saveimg
         self.scales = scales.split(",") if isinstance(scales, str) else [str(s) for s in scales]
         self.n_itrs = [int(n) for n in n_itrs.split(",")] if isinstance(n_itrs, str) else [int(n) for n in n_itrs]
         if len(self.scales) != len(self.n_itrs):
@@ -186,6 +190,11 @@ class Registrar:
 
     # ------------------------------------------------------------------ public API
     def run(self, gt, init_pose, intrinsics=None, verbose=False):
+        if len(init_pose) != 1 or gt.shape[0] != 1:
+            # the fused update kernel (csrc/regstep.cu) and the trajectory rows are laid out for one pose, as the
+            # reference's loop is (one X-ray per `xvr register` call, base.py:198-292)
+            raise ValueError(f"Registrar.run registers ONE X-ray to one pose; got {gt.shape[0]} image(s) and "
+                             f"{len(init_pose)} initial pose(s)")
         device = self.drr.device
         self.sim2.to(device)
         if intrinsics is not None:
@@ -260,6 +269,103 @@ class Registrar:
         times = [0.0] + [t for st in stage_times for t in st]
         return pose, dict(params=params, nccs=nccs, times=times, alphas=alphas, runtime=sum(times),
                           n_itrs=stage_counts)
+
+    # ------------------------------------------------------------------ results on disk
+    COLUMNS = ("r1", "r2", "r3", "tx", "ty", "tz", "ncc", "times", "lr_rot", "lr_xyz")
+
+    def register(self, gt, init_pose, intrinsics, outpath, name="xray", verbose=False):
+        """``_RegistrarBase.__call__`` (base.py:294-339) for an X-ray that is already a tensor: run, render the
+        initial / final DRRs if ``saveimg``, write ``<outpath>/<name>/parameters.pt``.  ``intrinsics`` are the
+        X-ray's own (sdd, height, width, delx, dely, x0, y0 as read from its DICOM); like the reference's ``run``
+        (base.py:141-149) the principal-point x offset is negated before it reaches the detector."""
+        from pathlib import Path  # noqa: PLC0415
+
+        applied = dict(intrinsics)
+        if "x0" in applied:
+            applied["x0"] = -applied["x0"]
+        final_pose, info = self.run(gt, init_pose, applied, verbose=verbose)
+        savepath = Path(outpath) / name
+        savepath.mkdir(parents=True, exist_ok=True)
+        init_img = final_img = None
+        if self.saveimg:
+            with torch.no_grad():
+                init_img = self.drr(init_pose.to(self.drr.device)).cpu()
+                final_img = self.drr(final_pose).cpu()
+        trajectory = self.trajectory(info)
+        self.save(savepath, gt, init_img, final_img, name, applied, init_pose.matrix.detach().cpu(),
+                  final_pose.matrix.detach().cpu(), dict(pf_to_af=None, runtime=info["runtime"], trajectory=trajectory))
+        return final_pose, info
+
+    def trajectory(self, info):
+        """The reference's ``_make_csv`` (base.py:410-423): one row per iteration with COLUMNS; a pandas DataFrame
+        when pandas is importable (as in the reference), else a dict of column -> list."""
+        import numpy as np  # noqa: PLC0415
+
+        table = np.concatenate([np.asarray(info["params"], dtype=np.float64),
+                                np.asarray(info["nccs"], dtype=np.float64)[:, None],
+                                np.asarray(info["times"], dtype=np.float64)[:, None],
+                                np.asarray(info["alphas"], dtype=np.float64)], axis=1)
+        try:
+            import pandas as pd  # noqa: PLC0415
+
+            return pd.DataFrame(table, columns=list(self.COLUMNS))
+        except ImportError:
+            return {c: table[:, i].tolist() for i, c in enumerate(self.COLUMNS)}
+
+    def save(self, savepath, gt, init_img, final_img, i2d, intrinsics, init_pose, final_pose, kwargs):
+        """Write ``parameters.pt`` with the keys of the reference's ``_RegistrarBase.save`` (base.py:341-399), so that
+        downstream scripts that read registration results (``torch.load(".../parameters.pt")["final_pose"]`` ...) work
+        unchanged; PNGs of the target / initial / final images with ``saveimg``."""
+        from pathlib import Path  # noqa: PLC0415
+
+        pv = self.provenance
+        as_path = lambda p: Path(p).resolve() if p is not None else None  # noqa: E731
+        renderer = pv.get("renderer", type(self.drr.renderer).__name__.lower())
+        parameters = {
+            "drr": {
+                "volume": as_path(pv.get("volume")),
+                "mask": as_path(pv.get("mask")),
+                "labels": pv.get("labels"),
+                "orientation": pv.get("orientation", "AP"),
+                **intrinsics,
+                "reverse_x_axis": pv.get("reverse_x_axis", self.drr.detector.reverse_x_axis),
+                "renderer": renderer,
+                "read_kwargs": pv.get("read_kwargs", {}),
+                "drr_kwargs": pv.get("drr_kwargs", {}),
+            },
+            "xray": {
+                "filename": as_path(i2d) if pv.get("xray_is_file", False) else i2d,
+                "crop": self.crop,
+                "subtract_background": pv.get("subtract_background", False),
+                "linearize": pv.get("linearize", True),
+                "reducefn": pv.get("reducefn", "max"),
+            },
+            "optimization": {
+                "equalize": self.equalize,
+                "init_only": False,
+                "scales": ",".join(self.scales),
+                "n_itrs": ",".join(str(n) for n in self.n_itrs),
+                "parameterization": self.parameterization,
+                "convention": self.convention,
+                "lr_rot": self.lr_rot,
+                "lr_xyz": self.lr_xyz,
+                "patience": self.patience,
+                "max_n_plateaus": self.max_n_plateaus,
+            },
+            "init_pose": init_pose,
+            "final_pose": final_pose,
+            **pv.get("save_kwargs", {}),
+            **kwargs,
+        }
+        torch.save(parameters, f"{savepath}/parameters.pt")
+        if self.saveimg:
+            from torchvision.utils import save_image  # noqa: PLC0415
+
+            save_image(gt, f"{savepath}/gt.png", normalize=True)
+            save_image(init_img, f"{savepath}/init_img.png", normalize=True)
+            if final_img is not None:
+                save_image(final_img, f"{savepath}/final_img.png", normalize=True)
+        return parameters
 
     # ------------------------------------------------------------------ CUDA graph
     def _capture(self, reg, transform, img, state, sched, log):

@@ -96,16 +96,25 @@ class _LabelCache:
     def get(self, mask):
         key = (mask.data_ptr(), mask._version, tuple(mask.shape), mask.dtype, mask.device)
         hit = self.entries.get(key)
+        # The key alone is not an identity: the reference's Trainer.load builds a fresh float mask every iteration
+        # (`mask.to(device, dtype)`), the caching allocator hands the freed block back, and the new tensor has the
+        # old pointer, shape and version 0.  An entry is a hit only while its SOURCE TENSOR OBJECT is alive and is
+        # the one asked about (the uint8 copy is kept alive by the entry, the source only weakly).
+        if hit is not None and hit[2]() is not mask:
+            self.entries.pop(key)
+            hit = None
         if hit is None:
             hi = int(mask.max().item())  # same host sync as the reference's `int(mask.max()) + 1`
             lo = int(mask.min().item())
             if lo < 0 or hi > 254:
                 raise _lib.XvrB200Error(f"label volume must hold integers in [0, 254]; got [{lo}, {hi}]")
+            for k in [k for k, v in self.entries.items() if v[2]() is None]:
+                self.entries.pop(k)  # sources that died
             while len(self.entries) >= self.MAX_ENTRIES:
                 self.entries.pop(next(iter(self.entries)))
-            hit = (mask.to(torch.uint8).contiguous(), hi + 1)
+            hit = (mask.to(torch.uint8).contiguous(), hi + 1, weakref.ref(mask))
             self.entries[key] = hit
-        return hit
+        return hit[0], hit[1]
 
 
 def _check_rays(volume, source, target, raylen):
@@ -149,7 +158,7 @@ class _RenderRays(torch.autograd.Function):
         vol_args = (ptr(volume),) if voltex is False else (ptr(volume), voltex)
         ctx.common = (*vol_args, *volume.shape, ptr(labels), C, ptr(source), ptr(target), ptr(raylen), B, N, *args,
                       det_h, det_w, lw, cw)
-        call(f"xvr_{kind}_rays_fwd", *ctx.common, ptr(out), ptr(jac), stream())
+        call(f"xvr_{kind}_rays_fwd", *ctx.common, ptr(out), ptr(jac), _lib.opts_word(), stream())
         ctx.kind = kind
         if need_pose_grad:
             # the recompute path (per-channel upstream gradients) needs the inputs; saving them keeps the raw
@@ -177,7 +186,7 @@ class _RenderRays(torch.autograd.Function):
                  ptr(work), stream())
         else:
             call(f"xvr_{ctx.kind}_rays_bwd", *ctx.common, ptr(gout), ptr(gsource), ptr(gtarget), ptr(graylen),
-                 ptr(work), stream())
+                 ptr(work), *((_lib.opts_word(),) if ctx.kind == "siddon" else ()), stream())
         return None, gsource, gtarget, graylen, None, None, None, None, None, None
 
 
@@ -192,8 +201,11 @@ class _RenderDRR(torch.autograd.Function):
     if the volume requires a gradient, gathers dL/dvolume voxel by voxel (no atomics, deterministic)."""
 
     @staticmethod
-    def forward(ctx, volume, cam2vox, cam2world, det9, det_hw, args, voltex):
+    def forward(ctx, volume, cam2vox, cam2world, det9, det_hw, kind, args, voltex):
         cam2vox, cam2world = cuda_f32(cam2vox, "cam2vox"), cuda_f32(cam2world, "cam2world")
+        if kind == "siddon" and ctx.needs_input_grad[0]:
+            raise _lib.XvrB200Error("d/dvolume of the Siddon renderer goes through the ray entry point "
+                                    "(drr.renderer(volume, source, target, raylen))")
         B = cam2vox.shape[0]
         H, W = det_hw
         lw, cw = _tile_shape()
@@ -205,14 +217,17 @@ class _RenderDRR(torch.autograd.Function):
             ctx.save_for_backward(jac)
             return out
         staged = os.environ.get("XVR_B200_STAGED", "0")
-        if staged in ("1", "2"):
+        if kind == "siddon":
+            call("xvr_siddon_drr_fwd", ptr(volume), *volume.shape, ptr(cam2vox), ptr(cam2world), det, B, H, W, *args,
+                 lw, cw, ptr(out), ptr(jac), _lib.opts_word(), stream())
+        elif staged in ("1", "2"):
             # opt-in, not yet run on a GPU: bricks staged in shared memory by TMA bulk copies, single (1) or double
             # (2) buffered (csrc/trilinear_staged.cu)
             call("xvr_trilinear_drr_fwd_staged", ptr(volume), *volume.shape, ptr(cam2vox), ptr(cam2world), det, B, H, W,
                  *args, int(staged), ptr(out), ptr(jac), ptr(_staged_stats.get("tensor")), stream())
         else:
             call("xvr_trilinear_drr_fwd", ptr(volume), voltex, *volume.shape, ptr(cam2vox), ptr(cam2world), det, B, H,
-                 W, *args, lw, cw, ptr(out), ptr(jac), stream())
+                 W, *args, lw, cw, ptr(out), ptr(jac), _lib.opts_word(), stream())
         ctx.det = (det, B, H, W, args, tuple(volume.shape))
         ctx.save_for_backward(jac, *((cam2vox, cam2world) if ctx.needs_input_grad[0] else ()))
         return out
@@ -226,7 +241,7 @@ class _RenderDRR(torch.autograd.Function):
         if B == 0:
             return (torch.zeros(shape, device=gout.device) if ctx.needs_input_grad[0] else None,
                     torch.zeros(0, 3, 4, device=gout.device) if ctx.needs_input_grad[1] else None,
-                    None, None, None, None, None)
+                    None, None, None, None, None, None)
         if ctx.needs_input_grad[1]:
             gG = torch.empty(B, 3, 4, device=gout.device, dtype=torch.float32)
             slices = _lib.lib().xvr_drr_jac_bwd_slices(B, H * W)
@@ -241,8 +256,8 @@ class _RenderDRR(torch.autograd.Function):
             work = torch.empty(B * H * W * 12, device=gout.device, dtype=torch.float32)
             gvol = torch.empty(shape, device=gout.device, dtype=torch.float32)
             call("xvr_trilinear_drr_bwd_volume", ptr(cam2vox), ptr(vox2cam), ptr(cam2world), det, B, H, W, *args,
-                 ptr(gout), *shape, ptr(work), ptr(gvol), 0, stream())
-        return gvol, gG, None, None, None, None, None
+                 ptr(gout), *shape, ptr(work), ptr(gvol), 0, _lib.opts_word(), stream())
+        return gvol, gG, None, None, None, None, None, None
 
 
 class Trilinear(torch.nn.Module):
@@ -281,7 +296,7 @@ class Trilinear(torch.nn.Module):
         volume = cuda_f32(volume, "volume")
         origin, row_step, col_step = detector.pixel_basis()
         return _RenderDRR.apply(volume, cam2vox, cam2world, (*origin, *row_step, *col_step),
-                                (detector.height, detector.width),
+                                (detector.height, detector.width), "trilinear",
                                 (int(n_points), conv.STEP_MODES[self.step], float(self.eps)),
                                 self._texture.get(volume))
 
@@ -309,3 +324,11 @@ class Siddon(torch.nn.Module):
         labels, C = (None, 1) if mask is None else self._labels.get(mask)
         return _RenderRays.apply(cuda_f32(volume, "volume"), source, target, img, labels, C, "siddon",
                                  (float(self.voxel_shift), float(self.eps)), self.detector_hw, False)
+
+    def render_drr(self, volume, cam2vox, cam2world, detector):
+        """Fused path used by ``DRR.forward``: rays are generated inside the kernel (no (B,N,3) tensors)."""
+        volume = cuda_f32(volume, "volume")
+        origin, row_step, col_step = detector.pixel_basis()
+        return _RenderDRR.apply(volume, cam2vox, cam2world, (*origin, *row_step, *col_step),
+                                (detector.height, detector.width), "siddon",
+                                (float(self.voxel_shift), float(self.eps)), None)

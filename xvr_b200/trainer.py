@@ -202,23 +202,15 @@ class TrainStep:
             self._init_graph_mode(lr)
 
     # ------------------------------------------------------------------ pieces
-    def _standardize(self, x):
-        """XrayTransforms with the batch-global min/max of the UNSHARDED batch (utils/preprocess.py:28-29)."""
-        if not self.standardize_global:
-            return self.transforms(x)
-        lo, hi = x.detach().min(), x.detach().max()
-        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
-        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
-        x = (x - lo) / (hi - lo + 1e-6)
-        t = self.transforms
-        if tuple(x.shape[-2:]) != t.size:
-            x = torch.nn.functional.interpolate(x, size=t.size, mode="bilinear", align_corners=False, antialias=True)
-        return (x - t.mean) / t.std
-
     def _allreduce_grads(self):
         if self.world == 1:
             return
-        grads = [p.grad for p in self.model.parameters() if p.grad is not None]
+        # every rank reduces EVERY parameter: a rank whose whole accumulation window kept no sample has no .grad
+        # tensors yet and contributes zeros (a rank-dependent parameter list would mismatch the collective)
+        for p in self.model.parameters():
+            if p.grad is None:
+                p.grad = torch.zeros_like(p)
+        grads = [p.grad for p in self.model.parameters()]
         flat = torch.cat([g.reshape(-1) for g in grads])
         dist.all_reduce(flat, op=dist.ReduceOp.SUM)  # NCCL over NVLink; ~45 MB for ResNet-18
         offset = 0
@@ -239,6 +231,8 @@ class TrainStep:
     def step(self, itr):
         if self.use_cuda_graph:
             return self._step_graphed(itr)
+        if self.world > 1:
+            return self._step_masked_eager(itr)
         dev = self.device
         subject, contrast, rot, xyz = self._draw(itr)
         vol, seg, affinv, offset = self.volumes[subject]
@@ -251,23 +245,21 @@ class TrainStep:
             img, mask, keep = render_samples(self.drr, density, seg, affinv, pose)
         img, mask, pose = img[keep], mask[keep], pose[keep]
 
+        # single rank: the reference's dynamic shapes (samples that miss the volume are indexed away).  Several ranks
+        # never come here: a rank-local `if len(pose) > 0` around collectives would mismatch them whenever one rank
+        # keeps nothing, so they run the masked, static-shape iteration (_step_masked_eager) instead.
         kept = torch.tensor([float(keep.sum())], device=dev)
-        if self.world > 1:
-            dist.all_reduce(kept, op=dist.ReduceOp.SUM)
         log = {"kept": kept.item() / self.batch_size}
         if len(pose) > 0:
-            x = self._standardize(img)
+            x = self.transforms(img)
             pred_pose = self.model(x)
             pred_img, pred_mask, _ = render_samples(self.drr, density, seg, affinv, pred_pose)
-            x_true, x_pred = x, self._standardize(pred_img)
+            x_true, x_pred = x, self.transforms(pred_img)
             loss, mncc, dgeo, rgeo, tgeo, dice, mvc = self.lossfn(x_true, mask, pose, x_pred, pred_mask, pred_pose)
-            # global mean over the kept samples of ALL ranks, scaled for gradient accumulation
             (loss.sum() / kept.clamp_min(1.0) / self.n_grad_accum_itrs).backward()
             sums = torch.stack([loss.sum(), mncc.sum(), dgeo.sum(), rgeo.sum(), tgeo.sum(), dice.sum()]).detach()
         else:
             sums = torch.zeros(6, device=dev)
-        if self.world > 1:
-            dist.all_reduce(sums, op=dist.ReduceOp.SUM)
         means = (sums / kept.clamp_min(1.0)).tolist()
         means[0] /= self.n_grad_accum_itrs  # the reference logs the loss after dividing it for accumulation
         log.update(dict(zip(("loss", "mncc", "dgeo", "rgeo", "tgeo", "dice"), means)))
@@ -286,8 +278,38 @@ class TrainStep:
         from .inference import save_checkpoint  # noqa: PLC0415
 
         if self.rank == 0:
-            save_checkpoint(path, self.model, self.optimizer, self.scheduler, itr, model_number, config)
+            optimizer, scheduler = self.optimizer, self.scheduler
+            if self.use_cuda_graph:
+                optimizer, scheduler = self._portable_optimizer_state()
+            save_checkpoint(path, self.model, optimizer, scheduler, itr, model_number, config)
         return path
+
+    def _portable_optimizer_state(self):
+        """Graph mode drives a capturable Adam with a device-side learning rate by hand; the reference's
+        ``reuse_optimizer`` resume expects the state of a plain Adam + its scheduler.  Returns objects whose
+        ``state_dict()`` is exactly that: float learning rates, CPU step counters, and a scheduler whose counters
+        (``last_epoch``, ``_last_lr``, ``_step_count``) stand where ``_opt_steps`` optimiser steps leave them."""
+        lr_now = self._base_lr * self._lr_factor(self._opt_steps)
+        sd = self.optimizer.state_dict()
+        for g in sd["param_groups"]:
+            g["lr"] = lr_now
+            g["capturable"] = False
+            g["initial_lr"] = self._base_lr  # what a scheduler attached to the optimizer records
+        for st in sd["state"].values():
+            if torch.is_tensor(st.get("step")):
+                st["step"] = st["step"].detach().to("cpu", torch.float32)
+        self.scheduler.last_epoch = self._opt_steps
+        self.scheduler._step_count = self._opt_steps + 1
+        self.scheduler._last_lr = [lr_now for _ in self.scheduler.optimizer.param_groups]
+
+        class _State:  # state_dict() carrier
+            def __init__(self, d):
+                self._d = d
+
+            def state_dict(self):
+                return self._d
+
+        return _State(sd), self.scheduler
 
     # ------------------------------------------------------------------ the iteration as CUDA graphs
     # The eager iteration above costs ~20 ms of host time (a ResNet forward/backward, two renders, ~10^3 small
@@ -322,12 +344,36 @@ class TrainStep:
             x = torch.nn.functional.interpolate(x, size=t.size, mode="bilinear", align_corners=False, antialias=True)
         return (x - t.mean) / t.std
 
+    def _step_masked_eager(self, itr):
+        """The eager iteration of a multi-rank run: static shapes (dropped samples keep their slot with weight 0), so
+        that every rank issues the same collectives whatever it kept -- the same arithmetic as graph mode, without
+        the capture."""
+        dev = self.device
+        subject, contrast, rot, xyz = self._draw(itr)
+        log_dev = self._masked_iteration(subject, rot.to(dev), xyz.to(dev), contrast, None)
+        if (itr + 1) % self.n_grad_accum_itrs == 0 or (itr + 1) == self.n_total_itrs:
+            self._allreduce_grads()
+            adaptive_clip_grad_(self.model.parameters())
+            self.optimizer.step()
+            self.scheduler.step()
+            self.optimizer.zero_grad()
+        log = dict(zip(("loss", "mncc", "dgeo", "rgeo", "tgeo", "dice", "kept"), log_dev.tolist()))
+        log["lr"] = self.scheduler.get_last_lr()[0]
+        return log
+
     def _device_iteration(self, subject):
+        vol = self.volumes[subject][0]
+        self._log.copy_(self._masked_iteration(subject, self._rot, self._xyz, self._contrast,
+                                               self._density_buffer(vol)))
+
+    def _masked_iteration(self, subject, rot, xyz, contrast, density_out):
+        """One iteration with static shapes; returns the 7 log values (loss, mncc, dgeo, rgeo, tgeo, dice, kept
+        fraction) as a device tensor.  ``contrast`` is a float or a 1-element device tensor."""
         vol, seg, affinv, offset = self.volumes[subject]
-        pose = convert(self._rot, self._xyz, parameterization="euler_angles", convention="ZXY", degrees=True)
+        pose = convert(rot, xyz, parameterization="euler_angles", convention="ZXY", degrees=True)
         pose = pose.compose(offset)
-        density = transform_hu_to_density(vol, self._contrast, out=self._density_buffer(vol))
-        if hasattr(self.drr.renderer, "_texture"):
+        density = transform_hu_to_density(vol, contrast, out=density_out)
+        if density_out is not None and hasattr(self.drr.renderer, "_texture"):
             self.drr.renderer._texture.invalidate()  # the buffer is rewritten through its raw pointer: upload again
         with torch.no_grad():
             img, mask, keep = render_samples(self.drr, density, seg, affinv, pose)
@@ -348,7 +394,7 @@ class TrainStep:
                 dist.all_reduce(sums, op=dist.ReduceOp.SUM)
             means = sums / denom
             means[0] /= self.n_grad_accum_itrs  # the reference logs the loss after dividing it for accumulation
-            self._log.copy_(torch.cat([means, kept / self.batch_size]))
+            return torch.cat([means, kept / self.batch_size])
 
     def _device_optimizer_step(self):
         self._allreduce_grads()
@@ -380,6 +426,13 @@ class TrainStep:
         self._base_lr = lr
         self._lr = torch.tensor(lr * self._lr_factor(0), device=dev, dtype=torch.float32)
         self.optimizer = torch.optim.Adam(self.model.parameters(), lr=self._lr, capturable=True)
+        # the scheduler object is only a carrier of the state the checkpoint needs (never stepped in graph mode):
+        # keep it on a plain Adam so that its state_dict is the one the reference's resume expects
+        carrier = torch.optim.Adam(self.model.parameters(), lr=lr)
+        if self._schedule is None:
+            self.scheduler = torch.optim.lr_scheduler.LambdaLR(carrier, lambda step: 1.0)
+        else:
+            self.scheduler = WarmupCosineSchedule(carrier, self.scheduler.warmup_steps, self.scheduler.t_total)
         for p in self.model.parameters():  # static .grad tensors shared by every graph
             p.grad = torch.zeros_like(p)
         # pinned staging ring for the per-step pose batch: the host may run several steps ahead of the device
