@@ -328,9 +328,9 @@ def run_config(name, steps, warmup, rank, world, device, with_clocks=True):
         keep[slot] = (img, g6)  # keep the device tensors alive until their copy has run
         if i > 0:  # the caller reads the previous step's result while this one renders
             done[slot ^ 1].synchronize()
-            checksum += float(img_hh[slot ^ 1][0, 0, H // 2, W // 2]) + float(grad_hh[slot ^ 1][0, 0])
+            checksum += float(img_hh[slot ^ 1][0, 0, H // 2, W // 2].detach()) + float(grad_hh[slot ^ 1][0, 0])
     done[(steps - 1) & 1].synchronize()
-    checksum += float(img_hh[(steps - 1) & 1][0, 0, H // 2, W // 2])
+    checksum += float(img_hh[(steps - 1) & 1][0, 0, H // 2, W // 2].detach())
     e3.record()
     barrier()
     assert checksum == checksum, "e2e result is NaN"
@@ -363,7 +363,7 @@ def run_config(name, steps, warmup, rank, world, device, with_clocks=True):
         alg = n_seg * 4 + B * H * W * 4  # one 4-byte voxel per traversed segment + the output pixel
         alg_note = (f"sum over rays of (n_seg*4+4): {n_seg} traversed segments in the batch "
                     f"({n_seg / (B * H * W):.1f} per ray), counted by xvr_siddon_trace")
-        kernel = "siddon_fwd_walk_kernel<JAC=true> (traversal + per-ray pose Jacobian in one pass)"
+        kernel = "siddon_fwd_kernel<JAC=true> (traversal + per-ray pose Jacobian in one pass)"
         two_pass = 2.0
     k_ms = kernel_ms.get(entry, [])
     k_avg = sum(k_ms) / len(k_ms) if k_ms else float("nan")

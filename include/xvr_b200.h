@@ -25,7 +25,7 @@ extern "C" {
  * library default; unknown bits are an invalid argument.  (ABI 1 had process-global setters for these.) */
 #define XVR_OPT_KSPLIT(log2) ((log2) + 1) /* trilinear forward: 2^log2 (0..3) lanes share one ray; 0 in the field = automatic
                                            * (small batches, B = 1 registration, split rays so that the SMs stay full) */
-#define XVR_OPT_SIDDON_CHECKED 0x10       /* Siddon: certified evaluation of every voxel index instead of the integer walk */
+#define XVR_OPT_SIDDON_WALK 0x10          /* Siddon: voxel indices from the integer walk (opt-in: same indices, measured slower) */
 #define XVR_OPT_VOLGRAD_GATHER 0x20       /* dL/dvolume: voxel-centric gather (cross-check) instead of the brick-local scatter */
 #define XVR_OPT_SIDDON_TOL(code) ((code) << 8) /* test hook: tolerance of the fast voxel-index certificate; 0 production,
                                            * 1 always the reference's exact arithmetic, 2/3/4 = x 1/2, 1/4, 1/8 (margin probes) */
@@ -53,12 +53,15 @@ int xvr_trilinear_rays_fwd(const float* volume, const void* voltex, int D0, int 
                            int n_points, int step_mode, float eps, int det_h, int det_w, int lane_w_log2,
                            int cta_w_log2, float* out, float* jac, int opts, void* stream);
 /* autograd backward of the above (= grid_sample backward + glue): re-marches the rays.
- *   gout (B,C,N) -> gsource (B,1,3), gtarget (B,N,3), graylen (B,N); workspace (B,3,N) */
+ *   gout (B,C,N) -> gsource (B,1,3), gtarget (B,N,3), graylen (B,N); workspace (B,3,N);
+ *   gvol NULL, or (D0,D1,D2) that dL/dvolume is ADDED to: the reference's own scatter (one RED.ADD per corner,
+ *   grid_sampler_3d_backward's safe_add_3d) -- rays given as tensors carry no detector geometry to derive an
+ *   atomics-free ownership from (the fused path has one: xvr_trilinear_drr_bwd_volume) */
 int xvr_trilinear_rays_bwd(const float* volume, const void* voltex, int D0, int D1, int D2, const uint8_t* labels,
                            int C, const float* source, const float* target, const float* raylen, int B, int N,
                            int n_points, int step_mode, float eps, int det_h, int det_w, int lane_w_log2,
                            int cta_w_log2, const float* gout, float* gsource, float* gtarget, float* graylen,
-                           float* workspace, void* stream);
+                           float* workspace, float* gvol, void* stream);
 /* backward through a Jacobian saved by a *_rays_fwd call: 28 bytes per ray instead of a second march */
 int xvr_rays_jac_bwd(const float* jac, const float* gout, int B, int N, float* gsource, float* gtarget,
                      float* graylen, float* workspace, void* stream);
@@ -85,15 +88,17 @@ int xvr_trilinear_drr_bwd_volume(const float* cam2vox, const float* vox2cam, con
                                  const float* det9, int B, int det_h, int det_w, int n_points, int step_mode,
                                  float eps, const float* gout, int D0, int D1, int D2, float* workspace, float* gvol,
                                  int accumulate, int opts, void* stream);
-/* Opt-in variant of xvr_trilinear_drr_fwd (NOT yet run on a GPU, csrc/trilinear_staged.cu): 16x16 detector tiles
- * march the volume slab by slab, each slab's brick staged in shared memory by cp.async.bulk (TMA) behind an mbarrier;
- * same arithmetic and summation order, so out / jac are bit-identical to xvr_trilinear_drr_fwd.  stages: 1 = one
- * staging buffer, 2 = double-buffered (copies of slab t+1 overlap the march of slab t).  stats: NULL or a zeroed
- * DEVICE unsigned long long[3] = {samples served from shared memory, from global memory, barrier time-outs}. */
+/* Variant of xvr_trilinear_drr_fwd with the volume staged brick by brick in shared memory by the TMA unit
+ * (csrc/trilinear_staged.cu): a CTA owns a detector tile of one pose, a producer warp issues one
+ * cp.async.bulk.tensor.3d per stage of the tile's frustum into a ring of shared-memory stages (hardware zero fill =
+ * grid_sample's zero padding), consumer warps interpolate from 8 shared-memory loads per sample.  Same arithmetic and
+ * summation order, so out / jac are bit-identical to xvr_trilinear_drr_fwd.  Needs a 16-byte aligned volume with
+ * D2 % 4 == 0.  stats: NULL or a zeroed DEVICE unsigned long long[3] = {samples served from shared memory, from global
+ * memory, barrier time-outs}. */
 int xvr_trilinear_drr_fwd_staged(const float* volume, int D0, int D1, int D2, const float* cam2vox,
                                  const float* cam2world, const float* det9, int B, int det_h, int det_w, int n_points,
-                                 int step_mode, float eps, int stages, float* out, float* jac,
-                                 unsigned long long* stats, void* stream);
+                                 int step_mode, float eps, float* out, float* jac, unsigned long long* stats,
+                                 void* stream);
 /* (two formulations, both atomics-free and deterministic, same result: brick-local scatter in shared memory by
  * default, voxel-centric gather with XVR_OPT_VOLGRAD_GATHER; csrc/volgrad.cu) */
 
@@ -113,17 +118,25 @@ int xvr_siddon_rays_bwd(const float* volume, int D0, int D1, int D2, const uint8
                         const float* source, const float* target, const float* raylen, int B, int N,
                         float voxel_shift, float eps, int det_h, int det_w, int lane_w_log2, int cta_w_log2,
                         const float* gout, float* gsource, float* gtarget, float* graylen, float* workspace,
-                        int opts, void* stream);
+                        float* gvol /* NULL, or (D0,D1,D2) accumulated into: one RED.ADD per segment */, int opts,
+                        void* stream);
+/* dL/dvolume of xvr_siddon_drr_fwd, atomics-free and deterministic (csrc/siddon_volgrad.cu): a warp owns a 16^3 brick
+ * of the gradient in shared memory, projects it onto the detector and lets the rays of that pixel window walk the
+ * part of their traversal inside the brick -- same crossings and certified voxel indices as the forward; lanes work
+ * on rays far enough apart never to meet in a voxel.  vox2cam (B,3,4) = inverse of cam2vox; gvol (+)= gradient. */
+int xvr_siddon_drr_bwd_volume(const float* cam2vox, const float* vox2cam, const float* cam2world, const float* det9,
+                              int B, int det_h, int det_w, float voxel_shift, float eps, const float* gout, int D0,
+                              int D1, int D2, float* gvol, int accumulate, int opts, void* stream);
 /* the traversal itself (test hook, and bench.py's segment count): idx/seg (B,N,trace_max), count (B,N);
  * trace_max = 0 with idx = seg = NULL writes the per-ray segment counts only */
 int xvr_siddon_trace(const float* volume, int D0, int D1, int D2, const float* source, const float* target, int B,
                      int N, float voxel_shift, float eps, int trace_max, int32_t* idx, float* seg, int32_t* count,
                      int opts, void* stream);
-/* Voxel index of a segment: by default the forward (without label channels) and trace kernels take it from an integer
- * walk (+-stride at every plane crossing) whenever min_a |d_a| * segment length / 2 exceeds the rounding budget of the
- * certified evaluation -- one multiply + compare instead of the three-axis evaluation, provably the same index
- * (scripts/siddon_cheap_certificate.py; bit-exact on the B200 against the oracle's reconstruction of the reference's
- * indices, tests/test_siddon_gpu.py).  XVR_OPT_SIDDON_CHECKED evaluates every index the certified way. */
+/* Voxel index of a segment: the certified evaluation of the midpoint (default).  With XVR_OPT_SIDDON_WALK the forward
+ * (without label channels) and trace kernels take it from an integer walk (+-stride at every plane crossing) whenever
+ * min_a |d_a| * segment length / 2 exceeds the rounding budget of the certified evaluation -- provably the same index
+ * (scripts/siddon_cheap_certificate.py; bit-exact on the B200, tests/test_siddon_gpu.py) but measured SLOWER at config 5
+ * (near-ties between axes fail the certificate in a third of the warp-wide iterations): kept as a cross-check. */
 
 /* test hook: the hoisted-reciprocal division of the traversal vs IEEE division on random operands;
  * mismatches is a DEVICE counter the caller zeroes */

@@ -66,7 +66,7 @@ def test_invalid_arguments_return_error_codes_not_crashes():
                           None, None) == -1
     assert b"xvr_regsim" in lib.xvr_last_error()
     # staged-brick renderer: one or two staging buffers, nothing else
-    assert lib.xvr_trilinear_drr_fwd_staged(None, 8, 8, 8, None, None, None, 1, 16, 16, 10, 0, 1e-8, 1, None, None, None,
+    assert lib.xvr_trilinear_drr_fwd_staged(None, 8, 8, 8, None, None, None, 1, 16, 16, 10, 0, 1e-8, None, None, None,
                                             None) == -1
     assert b"xvr_trilinear_drr_fwd_staged" in lib.xvr_last_error()
     # per-call options: unknown bits and out-of-range fields are invalid arguments, checked before any device work
@@ -513,7 +513,7 @@ def test_options_word_encoding():
     from xvr_b200._lib import options, opts_word
 
     assert opts_word() == 0
-    with options(ksplit=2, siddon_walk=False, volgrad="gather", siddon_tol="exact"):
+    with options(ksplit=2, siddon_walk=True, volgrad="gather", siddon_tol="exact"):
         assert opts_word() == (3 | 0x10 | 0x20 | (1 << 8))
     assert opts_word() == 0
     with pytest.raises(TypeError):

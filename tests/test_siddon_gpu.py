@@ -152,12 +152,12 @@ def test_fast_index_equals_exact_index(cuda, n, h, b, shift, stretch):
     assert cnt_f.sum().item() > 2_000_000
 
 
-# ------------------------------------------------------------------------------------------ integer walk (default)
+# ------------------------------------------------------------------------------------------ integer walk (opt-in)
 @pytest.mark.parametrize("walk", [True, False], ids=["walk", "checked"])
 @pytest.mark.parametrize("n,h,b,shift", [(64, 48, 4, 0.5), (40, 33, 3, 0.0), (256, 128, 2, 0.5)])
 def test_walk_and_checked_traversals_are_bit_exact(cuda, walk, n, h, b, shift):
-    """Both ways of obtaining a segment's voxel index -- the integer walk with its one-compare certificate (default)
-    and the certified three-axis evaluation (XVR_OPT_SIDDON_CHECKED) -- against the oracle's reconstruction of the
+    """Both ways of obtaining a segment's voxel index -- the certified three-axis evaluation (default) and the
+    integer walk with its one-compare certificate (XVR_OPT_SIDDON_WALK) -- against the oracle's reconstruction of the
     reference's indices."""
     import oracle
     from tests._scene import make_drr, pose_params

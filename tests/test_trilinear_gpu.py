@@ -166,7 +166,7 @@ def test_jacobian_and_recompute_backward_agree(cuda):
                         torch.empty(B, 1, N, device=cuda), torch.empty(B, 3, N, device=cuda))
     vol = drr.density
     call("xvr_trilinear_rays_bwd", ptr(vol), None, *vol.shape, None, 1, ptr(source), ptr(target), ptr(raylen), B, N, 500,
-         0, 1e-8, 32, 32, 3, 4, ptr(gout), ptr(gs), ptr(gt), ptr(gl), ptr(work), stream())
+         0, 1e-8, 32, 32, 3, 4, ptr(gout), ptr(gs), ptr(gt), ptr(gl), ptr(work), None, stream())
     assert rel_l2(gs, s.grad) < 1e-5
     assert rel_l2(gt, t.grad) < 1e-5
 

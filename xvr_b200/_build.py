@@ -7,10 +7,10 @@ from pathlib import Path
 
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
-LIB = PKG / "libxvr_b200.so"
+LIB = Path(os.environ["XVR_B200_LIB"]).resolve() if os.environ.get("XVR_B200_LIB") else PKG / "libxvr_b200.so"  # tuning variants
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-# siddon.cu must reproduce the reference's un-fused fp32 arithmetic bit for bit -> no FMA contraction there
-PER_FILE_FLAGS = {"siddon.cu": ["-fmad=false"]}
+# siddon*.cu must reproduce the reference's un-fused fp32 arithmetic bit for bit -> no FMA contraction there
+PER_FILE_FLAGS = {"siddon.cu": ["-fmad=false"], "siddon_volgrad.cu": ["-fmad=false"]}
 
 
 def sources():
@@ -27,7 +27,7 @@ def needs_build():
 
 def build(force=False, verbose=False):
     """Compile every .cu under csrc/ for sm_100a and link one shared library next to this file."""
-    if not force and not needs_build():
+    if os.environ.get("XVR_B200_LIB") or (not force and not needs_build()):
         return LIB
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):

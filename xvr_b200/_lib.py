@@ -26,12 +26,12 @@ _SIGNATURES = {
          c_int, P, P, c_int, P], c_int),
     "xvr_trilinear_rays_bwd": (
         [P, P, c_int, c_int, c_int, P, c_int, P, P, P, c_int, c_int, c_int, c_int, c_float, c_int, c_int, c_int,
-         c_int, P, P, P, P, P, P], c_int),
+         c_int, P, P, P, P, P, P, P], c_int),
     "xvr_trilinear_drr_fwd": (
         [P, P, c_int, c_int, c_int, P, P, ctypes.POINTER(c_float), c_int, c_int, c_int, c_int, c_int, c_float, c_int,
          c_int, P, P, c_int, P], c_int),
     "xvr_trilinear_drr_fwd_staged": (
-        [P, c_int, c_int, c_int, P, P, ctypes.POINTER(c_float), c_int, c_int, c_int, c_int, c_int, c_float, c_int, P, P,
+        [P, c_int, c_int, c_int, P, P, ctypes.POINTER(c_float), c_int, c_int, c_int, c_int, c_int, c_float, P, P,
          P, P], c_int),
     "xvr_drr_jac_bwd": ([P, P, ctypes.POINTER(c_float), c_int, c_int, c_int, P, P, P], c_int),
     "xvr_drr_jac_bwd_slices": ([c_int, c_int], c_int),
@@ -66,7 +66,10 @@ _SIGNATURES = {
          P, c_int, P], c_int),
     "xvr_siddon_rays_bwd": (
         [P, c_int, c_int, c_int, P, c_int, P, P, P, c_int, c_int, c_float, c_float, c_int, c_int, c_int, c_int, P, P,
-         P, P, P, c_int, P], c_int),
+         P, P, P, P, c_int, P], c_int),
+    "xvr_siddon_drr_bwd_volume": (
+        [P, P, P, ctypes.POINTER(c_float), c_int, c_int, c_int, c_float, c_float, P, c_int, c_int, c_int, P, c_int, c_int,
+         P], c_int),
     "xvr_selftest_division": ([c_int, c_int, ctypes.c_uint, P, P], c_int),
     "xvr_siddon_trace": (
         [P, c_int, c_int, c_int, P, P, c_int, c_int, c_float, c_float, c_int, P, P, P, c_int, P], c_int),
@@ -74,8 +77,8 @@ _SIGNATURES = {
 
 # ---- per-call kernel options (include/xvr_b200.h XVR_OPT_*).  The library itself keeps no mutable state: the
 # variant travels with every call.  This host-side holder only supplies the word; tests and tuning scripts change it
-# with `with options(siddon_walk=False): ...`.
-_OPTION_DEFAULTS = {"ksplit": None, "siddon_walk": True, "volgrad": "brick", "siddon_tol": "production"}
+# with `with options(siddon_walk=True): ...`.
+_OPTION_DEFAULTS = {"ksplit": None, "siddon_walk": False, "volgrad": "brick", "siddon_tol": "production"}
 _options = dict(_OPTION_DEFAULTS)
 _TOL_CODES = {"production": 0, "exact": 1, 0.5: 2, 0.25: 3, 0.125: 4}
 
@@ -86,7 +89,7 @@ def opts_word():
         if _options["ksplit"] not in (0, 1, 2, 3):
             raise ValueError("ksplit must be None (automatic) or 0..3 (log2 of the lanes per ray)")
         w |= _options["ksplit"] + 1
-    if not _options["siddon_walk"]:
+    if _options["siddon_walk"]:
         w |= 0x10
     if _options["volgrad"] == "gather":
         w |= 0x20
@@ -97,7 +100,7 @@ def opts_word():
 
 
 class options:
-    """Context manager: ``with options(siddon_walk=False, volgrad="gather"): ...``"""
+    """Context manager: ``with options(siddon_walk=True, volgrad="gather"): ...``"""
 
     def __init__(self, **kw):
         unknown = set(kw) - set(_OPTION_DEFAULTS)

@@ -13,7 +13,7 @@
 
 // Per-call options word `opts` of the entry points that have variants (include/xvr_b200.h XVR_OPT_*; 0 = default).
 #define XVR_OPT_KSPLIT_MASK 0x7        // 0: automatic, 1..4: 1/2/4/8 lanes share one ray (trilinear forward)
-#define XVR_OPT_SIDDON_CHECKED 0x10    // Siddon: every voxel index through the certified evaluation, no integer walk
+#define XVR_OPT_SIDDON_WALK 0x10       // Siddon: voxel indices from the integer walk where its certificate holds
 #define XVR_OPT_VOLGRAD_GATHER 0x20    // dL/dvolume: voxel-centric gather instead of the brick-local scatter
 #define XVR_OPT_SIDDON_TOL_SHIFT 8     // bits 8..11, test hook: certificate tolerance 0: x1, 1: always exact, 2..4: x1/2, 1/4, 1/8
 #define XVR_OPT_KNOWN 0xF37
@@ -120,8 +120,11 @@ __device__ __forceinline__ AlphaRange alpha_range(const float s[3], const float 
 }
 
 // torch.linspace(0, 1, n)[k] in fp32 (ATen RangeFactories: symmetric evaluation around the midpoint).
+// The upper half is ONE fused operation, spelled out so that every kernel (texture, staged, backward, volume
+// adjoint) forms bit-identical sample parameters whatever the compiler's contraction choices are.
+__device__ __forceinline__ float linspace_tail(float step, float r) { return __fmaf_rn(-step, r, 1.0f); }
 __device__ __forceinline__ float linspace01(int k, int n, float step) {
-  return (k < n / 2) ? step * (float)k : 1.0f - step * (float)(n - 1 - k);
+  return (k < n / 2) ? step * (float)k : linspace_tail(step, (float)(n - 1 - k));
 }
 
 // Trilinear blend of the 8 corner values c[x][y][z] at fractional offsets (fx, fy, fz): along z (contiguous), then
@@ -198,6 +201,32 @@ __device__ __forceinline__ float sample_trilinear(const Vol& v, float x, float y
     c111 = (x1 && y1 && z1) ? __ldg(p + v.s0 + v.s1 + 1) : 0.f;
   }
   return trilinear_interp<GRAD>(c000, c001, c010, c011, c100, c101, c110, c111, fx, fy, fz, g);
+}
+
+// Adjoint of sample_trilinear w.r.t. the volume: coef * (trilinear weight) into each of the 8 corners that lie inside
+// the volume (zero-padded corners receive nothing) -- grid_sampler_3d_backward's safe_add_3d
+// (ATen/native/cuda/GridSampler.cuh:263-280), one RED.ADD.F32 per corner.  Used by the ray entry points, which have
+// no detector geometry to derive an atomics-free ownership from (the fused DRR path has: csrc/volgrad.cu).
+__device__ __forceinline__ void scatter_trilinear(float* __restrict__ gvol, const Vol& v, float x, float y, float z,
+                                                  float coef) {
+  if (!(x > -1.f && x < (float)v.D0 && y > -1.f && y < (float)v.D1 && z > -1.f && z < (float)v.D2)) return;
+  const float fx0 = floorf(x), fy0 = floorf(y), fz0 = floorf(z);
+  const int ix = (int)fx0, iy = (int)fy0, iz = (int)fz0;
+  const float fx = x - fx0, fy = y - fy0, fz = z - fz0;
+  const float wx[2] = {1.f - fx, fx}, wy[2] = {1.f - fy, fy}, wz[2] = {1.f - fz, fz};
+#pragma unroll
+  for (int ox = 0; ox < 2; ++ox) {
+    if ((unsigned)(ix + ox) >= (unsigned)v.D0) continue;
+#pragma unroll
+    for (int oy = 0; oy < 2; ++oy) {
+      if ((unsigned)(iy + oy) >= (unsigned)v.D1) continue;
+#pragma unroll
+      for (int oz = 0; oz < 2; ++oz) {
+        if ((unsigned)(iz + oz) >= (unsigned)v.D2) continue;
+        atomicAdd(gvol + ((int64_t)(ix + ox) * v.s0 + (iy + oy) * v.s1 + (iz + oz)), coef * wx[ox] * wy[oy] * wz[oz]);
+      }
+    }
+  }
 }
 
 // Nearest label lookup at the same sampler coordinate (grid_sample mode="nearest", align_corners=True,

@@ -40,6 +40,7 @@ struct TrilinearParams {
   float* __restrict__ gtarget;     // (B,N,3)
   float* __restrict__ gsrc_ray;    // (B,3,N) per-ray source gradient (reduced by reduce_rows)
   float* __restrict__ graylen;     // (B,N)
+  float* __restrict__ gvol;        // (D0,D1,D2), accumulated into (ray entry point: RED.ADD scatter), nullable
 };
 
 __device__ __forceinline__ float step_weight(int mode, float span, int n) {
@@ -140,7 +141,7 @@ __global__ void __launch_bounds__(256, XVR_TRI_MIN_CTAS) trilinear_fwd_kernel(co
     for (; k < k1; ++k, kf += 1.0f) sample(lstep * kf);
     float rf = (float)(np - 1 - k);
     XVR_UNROLL(XVR_TRI_UNROLL)
-    for (; k < kend; ++k, rf -= 1.0f) sample(1.0f - lstep * rf);
+    for (; k < kend; ++k, rf -= 1.0f) sample(linspace_tail(lstep, rf));
   }
 
   if (ks > 0) {  // combine the slices (fixed order: deterministic); slice 0 writes
@@ -207,7 +208,7 @@ __global__ void __launch_bounds__(256, XVR_TRI_MIN_CTAS) trilinear_fwd_kernel(co
 // Recompute backward: given dL/dout (B,C,N) re-march every ray and emit dL/dtarget (B,N,3), the per-ray
 // dL/dsource (B,3,N) and dL/draylen (B,N).  Handles label channels (the upstream gradient of a sample is the
 // one of the channel its label selects).
-template <bool LABELS, bool TEX>
+template <bool LABELS, bool TEX, bool VOLGRAD>
 __global__ void __launch_bounds__(256) trilinear_bwd_kernel(const TrilinearParams p) {
   extern __shared__ float chan_g[];  // LABELS: [C][256] upstream gradient per channel
   const int b = blockIdx.x / p.tiles_per_pose;
@@ -258,6 +259,7 @@ __global__ void __launch_bounds__(256) trilinear_bwd_kernel(const TrilinearParam
       const float v = sample_trilinear<true, TEX>(p.vol, x, y, z, g);
       float go = g1;
       if (LABELS) go = chan_g[sample_label(p.labels, p.vol, x, y, z) * 256 + tid];
+      if (VOLGRAD) scatter_trilinear(p.gvol, p.vol, x, y, z, go * L * w);
       sumV = fmaf(go, v, sumV);
 #pragma unroll
       for (int a = 0; a < 3; ++a) {
@@ -553,7 +555,7 @@ extern "C" int xvr_trilinear_rays_bwd(const float* volume, const void* voltex, i
                                       const float* source, const float* target, const float* raylen, int B,
                                       int N, int n_points, int step_mode, float eps, int det_h, int det_w,
                                       int lane_w_log2, int cta_w_log2, const float* gout, float* gsource,
-                                      float* gtarget, float* graylen, float* workspace, void* stream) {
+                                      float* gtarget, float* graylen, float* workspace, float* gvol, void* stream) {
   TrilinearParams p = {};
   int rc = fill_common(p, volume, voltex, D0, D1, D2, labels, C, source, target, raylen, B, N, n_points, step_mode, eps,
                        det_h, det_w, lane_w_log2, cta_w_log2, 0, false);
@@ -566,17 +568,21 @@ extern "C" int xvr_trilinear_rays_bwd(const float* volume, const void* voltex, i
   p.gtarget = gtarget;
   p.gsrc_ray = workspace;  // (B,3,N)
   p.graylen = graylen;
+  p.gvol = gvol;
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t grid = (int64_t)B * p.tiles_per_pose;
   const size_t smem = labels ? (size_t)C * 256 * sizeof(float) : 0;
   const bool tex = p.vol.tex != 0;
-  if (labels) {
-    auto k = tex ? trilinear_bwd_kernel<true, true> : trilinear_bwd_kernel<true, false>;
+  auto launch = [&](auto k) {
     if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k<<<(unsigned)grid, 256, smem, st>>>(p);
+  };
+  if (labels) {
+    if (gvol) { if (tex) launch(trilinear_bwd_kernel<true, true, true>); else launch(trilinear_bwd_kernel<true, false, true>); }
+    else { if (tex) launch(trilinear_bwd_kernel<true, true, false>); else launch(trilinear_bwd_kernel<true, false, false>); }
   } else {
-    auto k = tex ? trilinear_bwd_kernel<false, true> : trilinear_bwd_kernel<false, false>;
-    k<<<(unsigned)grid, 256, 0, st>>>(p);
+    if (gvol) { if (tex) launch(trilinear_bwd_kernel<false, true, true>); else launch(trilinear_bwd_kernel<false, false, true>); }
+    else { if (tex) launch(trilinear_bwd_kernel<false, true, false>); else launch(trilinear_bwd_kernel<false, false, false>); }
   }
   rc = check_launch("xvr_trilinear_rays_bwd");
   if (rc) return rc;

@@ -1,43 +1,78 @@
-// Trilinear DRR forward (+ Jacobian) with the volume staged brick by brick in shared memory -- the variant
-// north_star describes ("TMA-staged volume bricks").  OPT-IN and NOT YET RUN ON A GPU (written after round 1's GPU
-// budget was spent; DESIGN.md 5.1, profiles/r1_brick_staging_model.md for the model that motivates it).
+// Trilinear DRR forward (+ Jacobian) with the volume staged brick by brick in shared memory by the TMA unit -- the
+// formulation north_star names ("TMA-staged volume bricks into shared memory").  Version 3 (round 2); the round-1
+// version (per-thread cp.async.bulk rows behind CTA-wide barriers) measured 40 ms per launch at config 2 against
+// 15.2 ms for the texture kernel and was dropped.
+//
+// STATUS (measured on the B200, profiles/r2_staged.md): bit-identical to the texture kernel on every parity case, 90-95 %
+// of the config-2 samples served from shared memory, no time-outs -- and 3.3x SLOWER than the texture kernel (49.4 ms
+// against 15.1 ms per 116-pose launch for the best tile / ring shape).  The reason is geometric, not a tuning gap: at
+// config 2 neighbouring rays are 1.4-2.8 voxels apart, so the axis-aligned box around a 16 x 16-ray frustum slab holds
+// 3-4 voxels per voxel that a sample actually touches (35-70 B of L2->SM fill per sample, 130-250 GB per launch,
+// against 79 GB for the texture path, which fetches only the footprints it needs).  OPT-IN (XVR_B200_STAGED=1); the
+// texture kernel stays the default.  It would pay on denser ray bundles (detector pixels <= one voxel apart).
 //
 // Same contract as xvr_trilinear_drr_fwd (csrc/trilinear.cu): same rays, same alpha_k, same sample positions, same
-// 8-corner blend (trilinear_interp) accumulated in the same order -- only the SOURCE of the 8 corners differs, so
-// the output must be bit-identical to the texture kernel's, which is what its tests assert.
+// 8-corner blend (trilinear_interp) accumulated in the same order -- only the SOURCE of the 8 corners differs, so the
+// output is bit-identical to the texture kernel's, which is what its tests assert.
 //
-// A CTA owns a 16 x 16 detector tile of one pose; warp w takes columns 2w, 2w+1 (16 rows x 2 columns per warp: the
-// detector rows run along the contiguous volume axis in the AP/PA set-up, so a warp's 8-corner loads spread over the
-// banks).  The tile's rays form a thin frustum; the CTA walks it slab by slab (ST_K voxel layers) along the
-// frustum's dominant volume axis A.  Per slab:
-//   1. warp 0 bounds the slab's corner indices on the other two axes from the four corner rays of the tile (the
-//      pixel -> plane-point map is projective, so the tile's image on a plane x_A = const is the convex hull of its
-//      corner images) and publishes the box;
-//   2. every thread issues the bulk copies (cp.async.bulk, the TMA unit's linear mode) of its rows of the box --
-//      a row is the box's extent along the contiguous axis, 16-byte aligned -- and zero-fills what lies outside the
-//      volume (= grid_sample's zero padding); completion is tracked by one mbarrier (expect-tx per thread);
-//   3. every thread interpolates those of its samples whose cell lies in the slab from 8 shared-memory loads.
-// Anything the box cannot serve is served from global memory with the reference arithmetic (sample_trilinear's
-// load path): boxes larger than the buffer, samples outside the box (rounding at its faces), rays that run
-// against the frustum's direction or only graze the zero padding, volumes whose rows are not 16-byte multiples,
-// and -- bounded spin -- a barrier that does not complete.  Nothing here can wait forever.
+// Structure.  A CTA owns a ST_TI x ST_TJ detector tile of one pose: NW consumer warps (one ray per thread, a warp =
+// ST_TI rows x 32/ST_TI columns) and ONE producer warp.  The tile's rays form a thin frustum that advances along its
+// dominant volume axis A; the frustum is cut into stages of ST_K cell layers (ST_K + 1 voxel layers).  The producer
+// bounds each stage's footprint on the other two axes from the tile's four corner rays (the pixel -> plane map is
+// projective, so the tile's image on a plane x_A = const is the convex hull of its corner images), picks the smallest
+// box of a fixed menu that covers it and issues ONE cp.async.bulk.tensor.3d (SASS UTMALDG) into a ring of ST_R
+// shared-memory stages; out-of-volume voxels are zero-filled by the TMA unit (= grid_sample's zero padding).
+// Completion is an mbarrier per ring slot (expect-tx); consumers never meet at a CTA-wide barrier: each warp walks
+// its samples k = 0..n-1 in lock step, waits for the stage its lanes are in, and publishes the lowest stage it
+// still needs in a shared progress word that the producer polls before it reuses a slot.
+// Anything a box cannot serve is served from global memory with the reference arithmetic (sample_trilinear's load
+// path): samples outside their box, rays that run against the frustum's direction, lanes that run more than a ring
+// ahead of their warp, boxes beyond the menu, and -- every wait is bounded -- a barrier that does not complete.
+#include <cuda.h>
+#include <stdio.h>
+
+#include <mutex>
+#include <unordered_map>
+
 #include "common.cuh"
 
 namespace xvr {
 
-// Tuning knobs (override with XVR_B200_NVCC_FLAGS="-DXVR_ST_K=8 -DXVR_ST_CAP=24576 -DXVR_ST_MIN_CTAS=2")
-#ifndef XVR_ST_K
-#define XVR_ST_K 4
+#ifndef XVR_ST_TI
+#define XVR_ST_TI 16  // tile rows = rays along a warp's lanes (16 or 32)
 #endif
-#ifndef XVR_ST_CAP
-#define XVR_ST_CAP 12288
+#ifndef XVR_ST_NW
+#define XVR_ST_NW 8  // consumer warps per CTA
+#endif
+#ifndef XVR_ST_K
+#define XVR_ST_K 4  // cell layers per stage (power of two)
+#endif
+#ifndef XVR_ST_R
+#define XVR_ST_R 2  // ring slots
 #endif
 #ifndef XVR_ST_MIN_CTAS
-#define XVR_ST_MIN_CTAS 3
+#define XVR_ST_MIN_CTAS 2
 #endif
-constexpr int ST_T = 16;             // detector tile edge per CTA
-constexpr int ST_K = XVR_ST_K;       // voxel layers per slab
-constexpr int ST_CAP = XVR_ST_CAP;   // floats in the staging buffer (48 KB -> three to four CTAs per SM)
+#ifndef XVR_ST_AREA
+#define XVR_ST_AREA 2560  // largest box footprint EP * EQ (floats per voxel layer)
+#endif
+constexpr int ST_TI = XVR_ST_TI;
+constexpr int ST_CPW = 32 / ST_TI;       // detector columns per warp
+constexpr int ST_NW = XVR_ST_NW;
+constexpr int ST_TJ = ST_NW * ST_CPW;    // tile columns
+constexpr int ST_NC = ST_NW * 32;        // consumer threads
+constexpr int ST_K = XVR_ST_K;
+constexpr int ST_KLOG = ST_K == 2 ? 1 : (ST_K == 4 ? 2 : 3);
+constexpr int ST_L = ST_K + 1;           // voxel layers per stage
+constexpr int ST_LP = (ST_L + 3) & ~3;   // ... padded to the TMA unit's 16-byte inner extent when the layers are innermost
+constexpr int ST_R = XVR_ST_R;
+constexpr int ST_AREA = XVR_ST_AREA;
+constexpr int ST_STAGE_FLOATS = ST_L * ST_AREA;
+constexpr int ST_MENU = 9;               // box extents 16, 24, ..., 80 on each lateral axis
+constexpr int ST_EMIN = 16, ESTEP = 8;
+static_assert((1 << ST_KLOG) == ST_K && ST_K % 4 == 0, "ST_K must be 4 or 8 (stage origins along axis 2 are 16-byte aligned)");
+static_assert(ST_TI == 16 || ST_TI == 32, "a warp covers 16 or 32 detector rows");
+static_assert((ST_STAGE_FLOATS * 4) % 128 == 0, "TMA destinations are 128-byte aligned");
 
 struct StagedParams {
   Vol vol;
@@ -45,15 +80,18 @@ struct StagedParams {
   int B, H, W, n_points, step_mode;
   float eps;
   int tiles_x, tiles_y;
-  float* __restrict__ out;          // (B,1,H*W)
-  float* __restrict__ jac;          // (B,7,H*W), nullable
-  unsigned long long* __restrict__ stats;  // nullable: {samples from shared memory, samples from global memory, barrier time-outs}
+  const CUtensorMap* __restrict__ maps;  // [3 axes][ST_MENU (EP)][ST_MENU (EQ)], device memory
+  float* __restrict__ out;               // (B,1,H*W)
+  float* __restrict__ jac;               // (B,7,H*W), nullable
+  unsigned long long* __restrict__ stats;  // nullable: {samples from shared memory, from global memory, time-outs}
 };
 
-struct BoxDesc {
-  int lo[3];   // first staged voxel index per axis (may be -1 / -4: zero padding)
-  int E[3];    // extent per axis; E[2] is a multiple of 4 and lo[2] a multiple of 4 (16-byte rows)
-  int staged;  // 0: this slab is served from global memory
+// One ring slot's box: lateral origin and strides of the voxel layout the TMA unit wrote.
+struct __align__(16) StageDesc {
+  int lo;      // loP | loQ << 16  (both biased by +4096 so that they are non-negative)
+  int sP;      // element stride of the first lateral axis
+  int sA;      // element stride of the marching axis
+  int lim;     // (EP - 1) | (EQ - 1) << 16, 0 when the stage is not staged (every sample fails the box test)
 };
 
 __device__ __forceinline__ float st_step_weight(int mode, float span, int n) {
@@ -67,7 +105,7 @@ __device__ __forceinline__ float st_step_weight_dspan(int mode, int n) {
   return 0.f;
 }
 
-// ---- mbarrier / bulk-copy wrappers (PTX ISA 8.x, sm_90+)
+// ---- mbarrier / TMA wrappers (PTX ISA 8.x, sm_90+)
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -89,59 +127,361 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return done != 0;
 }
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+      : "memory");
 }
 
-// component `a` of a 3-vector without dynamic indexing (keeps the arrays in registers)
-__device__ __forceinline__ float pick3(const float v[3], int a) { return a == 0 ? v[0] : (a == 1 ? v[1] : v[2]); }
+template <int A>
+struct Axes {  // the two lateral axes (ascending) and the element stride of the second one inside a staged box
+  static constexpr int P = A == 0 ? 1 : 0;
+  static constexpr int Q = A == 2 ? 1 : 2;
+  static constexpr int SQ = A == 2 ? ST_LP : 1;
+  static constexpr int LAYERS = A == 2 ? ST_LP : ST_L;  // voxel layers a staged box holds (A = 2: padded)
+};
 
-// slab number of a cell index (cells -ST_K .. -1 -> 0, 0 .. ST_K-1 -> 1, ...); first cell of slab n is (n-1)*ST_K
-__device__ __forceinline__ int slab_of(int cell) { return (max(cell, -ST_K) + ST_K) / ST_K; }
+struct CtaShared {
+  unsigned long long full[ST_R];  // mbarriers: slot filled
+  StageDesc desc[ST_R];
+  int progress[ST_NW];            // lowest stage each consumer warp still needs
+  int t_first, t_last;
+  int issued;                     // highest stage the producer has issued (its slot's previous load had completed)
+  int broken;                     // a wait timed out somewhere: everybody stops trusting the ring
+};
 
-template <bool JAC, int STAGES>
-__global__ void __launch_bounds__(256, STAGES == 1 ? XVR_ST_MIN_CTAS : 2) trilinear_fwd_staged_kernel(const StagedParams p) {
-  extern __shared__ __align__(16) float box[];  // STAGES * ST_CAP floats
-  __shared__ __align__(8) unsigned long long mbar_storage[2];
-  __shared__ BoxDesc descs[3];
-  __shared__ int t_first, t_last;
+// ---------------------------------------------------------------------------------------------------------------
+template <int A, bool JAC>
+__device__ __forceinline__ void consumer_march(const StagedParams& p, CtaShared& sh, const float* __restrict__ ring,
+                                               int tf, bool forward, bool regular, const float s[3], const float d[3],
+                                               float amin, float span, int warp, float& sumV, float Aj[3], float Uj[3],
+                                               unsigned& n_shared, unsigned& n_global, unsigned& n_timeout) {
+  using AX = Axes<A>;
+  const int np = p.n_points;
+  const float lstep = 1.0f / (float)(np - 1);
+  const int size_a = A == 0 ? p.vol.D0 : (A == 1 ? p.vol.D1 : p.vol.D2);
+  // travel index of cell c: forward c + ST_K (cells >= -1 stay non-negative), backward (size_a + ST_K - 1) - c;
+  // stage = travel index >> ST_KLOG; the stage's first REAL cell layer is the smaller end either way
+  const int off = forward ? ST_K : size_a + ST_K - 1;
+  const int sgn = forward ? 1 : -1;
+  const uint32_t full0 = smem_u32(&sh.full[0]);
+
+  int cur_t = INT_MIN;           // stage whose descriptor this lane holds
+  int d_lo = 0, d_sP = 0, d_sA = 0, d_lim = 0, d_first = 0;  // ... and the descriptor: origins, strides, limits, first layer
+  const float* d_base = ring;
+  int w_ready = tf - 1;          // highest stage this warp has seen filled (warp-uniform)
+  int w_rel = tf;                // progress published so far (warp-uniform)
+  bool trust = true;             // false once a wait timed out (CTA-wide flag mirrored per warp)
+#ifdef XVR_ST_DEBUG
+  int why = 0;
+#endif
+
+  if (!__any_sync(0xffffffffu, regular)) {  // nothing to march here: do not hold the producer back
+    if ((threadIdx.x & 31) == 0) *(volatile int*)&sh.progress[warp] = INT_MAX;
+    return;
+  }
+
+  // Every lane walks its own samples k = 0 .. np-1 in order.  Rays of a warp that enter and leave through the faces
+  // the frustum marches between stay at the same depth for the same k; rays clipped by a side face do not, so a lane
+  // whose next sample lies in a stage beyond the ring window STALLS (keeps its k) until the lanes behind it have
+  // caught up -- the lanes of the warp's lowest stage always proceed.
+  int k = 0;
+  while (__any_sync(0xffffffffu, regular && k < np)) {
+    const bool act = regular && k < np;
+    bool stall = false;
+    const float u = linspace01(min(k, np - 1), np, lstep);
+    const float alpha = fmaf(u, span, amin);
+    const float x = fmaf(alpha, d[0], s[0]);
+    const float y = fmaf(alpha, d[1], s[1]);
+    const float z = fmaf(alpha, d[2], s[2]);
+    const float fx0 = floorf(x), fy0 = floorf(y), fz0 = floorf(z);
+    const int ix = (int)fx0, iy = (int)fy0, iz = (int)fz0;
+    const int ca = A == 0 ? ix : (A == 1 ? iy : iz);
+    const int ip = AX::P == 0 ? ix : iy;
+    const int iq = AX::Q == 1 ? iy : iz;
+    const int tU = act ? (off + sgn * ca) >> ST_KLOG : cur_t;
+
+    if (__any_sync(0xffffffffu, tU != cur_t)) {
+      // ---- slow path, entered by the whole warp whenever a lane changes stage (every ~ST_K samples)
+      const int tmin = __reduce_min_sync(0xffffffffu, act ? tU : INT_MAX);
+      const int tmax = __reduce_max_sync(0xffffffffu, act ? tU : INT_MIN);
+      if (trust && tmin > w_rel) {  // stages below tmin are done with: let the producer reuse their slots
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) {
+          __threadfence_block();
+          *(volatile int*)&sh.progress[warp] = tmin;
+        }
+        w_rel = tmin;
+      }
+      // the ring holds stages w_rel .. w_rel + ST_R - 1: lanes beyond it are served from global memory
+      const int thi = min(tmax, tmin + ST_R - 1);
+      // stages below tmin are of no interest (and their slots may be several phases on): wait for tmin .. thi only,
+      // each of which cannot have been overwritten because this warp has not released it
+      w_ready = max(w_ready, tmin - 1);
+      while (trust && w_ready < thi) {
+        const int q = w_ready + 1 - tf;
+        const uint32_t bar = full0 + 8u * (uint32_t)(q % ST_R);
+        const uint32_t parity = (uint32_t)(q / ST_R) & 1u;
+        // A parity wait only means "use q / ST_R of this slot has completed" once the previous use is known to have
+        // completed -- else a warp that skipped that use (rays that start deep in the volume) would sail through a
+        // barrier that is still one phase behind.  The producer issues a stage only after its slot's previous load
+        // has landed, and says so in `issued`.
+        bool done = false;
+        for (int spin = 0; spin < (1 << 22) && !done; ++spin) {
+          done = *(volatile int*)&sh.issued >= w_ready + 1;
+          if (!done) __nanosleep(32);
+        }
+        if (done) {
+          done = false;
+          for (int spin = 0; spin < (1 << 20) && !done; ++spin) done = mbar_try_wait(bar, parity);
+        }
+        if (!done || *(volatile int*)&sh.broken) {
+          if (!done) {
+            *(volatile int*)&sh.broken = 1;
+            if ((threadIdx.x & 31) == 0) ++n_timeout;
+          }
+          trust = false;
+          break;
+        }
+        ++w_ready;
+      }
+      if (tU != cur_t && act) {
+#ifdef XVR_ST_DEBUG
+        why = (trust && tU <= w_ready) ? 0 : 2;
+#endif
+        if (trust && tU <= w_ready) {
+          const int slot = (tU - tf) % ST_R;
+          const int4 dd = *reinterpret_cast<const int4*>(&sh.desc[slot]);
+          d_lo = dd.x;
+          d_sP = dd.y;
+          d_sA = dd.z;
+          d_lim = dd.w;
+          d_base = ring + (size_t)slot * ST_STAGE_FLOATS;
+          // first real voxel layer of the stage: forward (tU << KLOG) - ST_K, backward size_a - 1 - (tU << KLOG) ... - (K - 1)
+          d_first = forward ? (tU << ST_KLOG) - ST_K : (size_a + ST_K - 1) - (tU << ST_KLOG) - (ST_K - 1);
+          cur_t = tU;
+#ifdef XVR_ST_DEBUG
+          if (d_lim == 0) why = 1;
+#endif
+        } else if (trust) {
+          stall = true;  // beyond the ring window: wait for the lanes behind (asks again next time round)
+        } else {
+          d_lim = 0;  // the ring is broken (a wait timed out): global memory from here on
+        }
+      }
+    }
+
+    float g[3], v;
+    const int lp = ip - ((d_lo & 0xffff) - 4096), lq = iq - ((int)((unsigned)d_lo >> 16) - 4096);
+    if (!act || stall) continue;
+    ++k;
+    if ((unsigned)lp < (unsigned)(d_lim & 0xffff) && (unsigned)lq < ((unsigned)d_lim >> 16)) {
+      const float* q0 = d_base + (ca - d_first) * d_sA + lp * d_sP + lq * AX::SQ;
+      const float* q1 = q0 + d_sA;  // next voxel layer along the marching axis
+      float c000, c001, c010, c011, c100, c101, c110, c111;
+      if (A == 0) {  // x = A, y = P, z = Q
+        c000 = q0[0]; c001 = q0[AX::SQ]; c010 = q0[d_sP]; c011 = q0[d_sP + AX::SQ];
+        c100 = q1[0]; c101 = q1[AX::SQ]; c110 = q1[d_sP]; c111 = q1[d_sP + AX::SQ];
+      } else if (A == 1) {  // x = P, y = A, z = Q
+        c000 = q0[0]; c001 = q0[AX::SQ]; c100 = q0[d_sP]; c101 = q0[d_sP + AX::SQ];
+        c010 = q1[0]; c011 = q1[AX::SQ]; c110 = q1[d_sP]; c111 = q1[d_sP + AX::SQ];
+      } else {  // x = P, y = Q, z = A
+        c000 = q0[0]; c010 = q0[AX::SQ]; c100 = q0[d_sP]; c110 = q0[d_sP + AX::SQ];
+        c001 = q1[0]; c011 = q1[AX::SQ]; c101 = q1[d_sP]; c111 = q1[d_sP + AX::SQ];
+      }
+      v = trilinear_interp<JAC>(c000, c001, c010, c011, c100, c101, c110, c111, x - fx0, y - fy0, z - fz0, g);
+      ++n_shared;
+    } else {
+      v = sample_trilinear<JAC, false>(p.vol, x, y, z, g);
+      ++n_global;
+#ifdef XVR_ST_DEBUG
+      if (p.stats) atomicAdd(p.stats + 4 + (why == 0 ? (d_lim == 0 ? 1 : 3) : why), 1ull);  // 5 unstaged, 6 ahead of ring, 7 box miss
+#endif
+    }
+    sumV += v;
+    if (JAC) {
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        Aj[a] += g[a];
+        Uj[a] = fmaf(u, g[a], Uj[a]);
+      }
+    }
+  }
+  // done: nothing of the ring is needed any more
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) {
+    __threadfence_block();
+    *(volatile int*)&sh.progress[warp] = INT_MAX;
+  }
+}
+
+// The producer warp: for every stage tf .. tl, wait until its ring slot is free, bound the box, issue the TMA load.
+template <int A>
+__device__ __forceinline__ void producer_loop(const StagedParams& p, CtaShared& sh, float* ring, int tf, int tl,
+                                              bool forward, int b, int i0, int j0) {
+  using AX = Axes<A>;
+  const int lane = threadIdx.x & 31;
+  const int size[3] = {p.vol.D0, p.vol.D1, p.vol.D2};
+  const int size_a = size[A];
+  // corner rays of the tile: lanes 0..3 (near plane of a stage) and 4..7 (far plane)
+  float qs[3] = {0.f, 0.f, 0.f}, qd[3] = {1.f, 1.f, 1.f};
+  if (lane < 8) {
+    const int ci = (lane & 1) ? min(i0 + ST_TI - 1, p.H - 1) : i0;
+    const int cj = (lane & 2) ? min(j0 + ST_TJ - 1, p.W - 1) : j0;
+    float ql;
+    generate_ray(p.geom, b, ci * p.W + cj, p.eps, qs, qd, ql);
+  }
+  const float qsA = qs[A], qdA = qd[A], qsP = qs[AX::P], qdP = qd[AX::P], qsQ = qs[AX::Q], qdQ = qd[AX::Q];
+  const uint32_t full0 = smem_u32(&sh.full[0]);
+  const bool aligned = ((size_t)p.vol.data & 15) == 0 && (size[2] & 3) == 0;
+
+  int issued = 0;
+  for (int t = tf; t <= tl; ++t, ++issued) {
+    const int q = t - tf;
+    const int slot = q % ST_R;
+    // ---- the slot is free once its previous load has landed (nobody may have waited for it: stages that no ray
+    // samples) and every consumer warp's progress has passed stage t - ST_R
+    if (q >= ST_R) {
+      {
+        const uint32_t bar = full0 + 8u * (uint32_t)slot;
+        const uint32_t parity = (uint32_t)(q / ST_R - 1) & 1u;
+        bool landed = false;
+        for (int spin = 0; spin < (1 << 22) && !landed; ++spin) landed = mbar_try_wait(bar, parity);
+        if (!landed) {
+          *(volatile int*)&sh.broken = 1;
+          break;
+        }
+      }
+      bool free_ = false;
+      for (int spin = 0; spin < (1 << 22) && !free_; ++spin) {
+        int pr = lane < ST_NW ? *(volatile int*)&sh.progress[lane] : INT_MAX;
+        pr = __reduce_min_sync(0xffffffffu, pr);
+        free_ = pr > t - ST_R;
+        if (!free_) {
+          if (*(volatile int*)&sh.broken) break;
+          __nanosleep(64);
+        }
+      }
+      if (!free_) {
+        *(volatile int*)&sh.broken = 1;
+        break;
+      }
+    }
+    // ---- box of stage t: real voxel layers first .. first + ST_K; lateral bounds from the corner rays on the planes
+    // that bound every sample whose cell lies in the stage
+    const int first = forward ? (t << ST_KLOG) - ST_K : (size_a + ST_K - 1) - (t << ST_KLOG) - (ST_K - 1);
+    float vP = 0.f, vQ = 0.f;
+    bool ok = true;
+    if (lane < 8) {
+      const float plane = (float)(first + ((lane & 4) ? ST_K : 0));
+      ok = fabsf(qdA) > 1e-12f;
+      const float al = ok ? (plane - qsA) / qdA : 0.f;
+      vP = fmaf(al, qdP, qsP);
+      vQ = fmaf(al, qdQ, qsQ);
+      ok = ok && al > 0.f && fabsf(vP) < 1e6f && fabsf(vQ) < 1e6f;
+    }
+    float mnP = lane < 8 ? vP : INFINITY, mxP = lane < 8 ? vP : -INFINITY;
+    float mnQ = lane < 8 ? vQ : INFINITY, mxQ = lane < 8 ? vQ : -INFINITY;
+    const unsigned bad = __ballot_sync(0xffffffffu, !ok);
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+      mnP = fminf(mnP, __shfl_xor_sync(0xffffffffu, mnP, o));
+      mxP = fmaxf(mxP, __shfl_xor_sync(0xffffffffu, mxP, o));
+      mnQ = fminf(mnQ, __shfl_xor_sync(0xffffffffu, mnQ, o));
+      mxQ = fmaxf(mxQ, __shfl_xor_sync(0xffffffffu, mxQ, o));
+    }
+    if (lane == 0) {
+      // a sample at lateral position v reads voxels floor(v), floor(v) + 1; nothing beyond one layer of zero
+      // padding is ever read (samples lie inside the volume)
+      const int loP = max((int)floorf(mnP), -1), hiP = min((int)floorf(mxP) + 1, size[AX::P]);
+      // The TMA unit faults (illegal instruction) unless the innermost tensor coordinate is 16-byte aligned
+      // (measured: scripts/tma_probe2.cu): the contiguous axis 2 is the second lateral axis when A = 0 or 1 -- align
+      // its origin down to a multiple of 4 voxels (-1 -> -4, two's complement) -- and the marching axis itself when
+      // A = 2, whose stage origins are multiples of ST_K given D2 % 4 == 0.
+      const int loQ = A == 2 ? max((int)floorf(mnQ), -1) : (max((int)floorf(mnQ), -1) & ~3);
+      const int hiQ = min((int)floorf(mxQ) + 1, size[AX::Q]);
+      const int nP = hiP - loP + 1, nQ = hiQ - loQ + 1;
+      const int mP = max(0, (nP - ST_EMIN + ESTEP - 1) / ESTEP), mQ = max(0, (nQ - ST_EMIN + ESTEP - 1) / ESTEP);
+      const int EP = ST_EMIN + ESTEP * mP, EQ = ST_EMIN + ESTEP * mQ;
+      const bool staged = aligned && bad == 0 && nP > 0 && nQ > 0 && mP < ST_MENU && mQ < ST_MENU &&
+                          AX::LAYERS * EP * EQ <= ST_STAGE_FLOATS;
+      StageDesc dsc;
+      dsc.lo = (loP + 4096) | ((loQ + 4096) << 16);
+      // layouts the TMA unit writes (innermost first): A=0 {Q, P, layer}, A=1 {Q, layer, P}, A=2 {layer, Q, P}
+      dsc.sP = A == 0 ? EQ : (A == 1 ? ST_L * EQ : ST_LP * EQ);
+      dsc.sA = A == 0 ? EP * EQ : (A == 1 ? EQ : 1);
+      dsc.lim = staged ? ((EP - 1) | ((EQ - 1) << 16)) : 0;
+      sh.desc[slot] = dsc;
+      const uint32_t bar = full0 + 8u * (uint32_t)slot;
+      if (staged) {
+        // the slot was read through the generic proxy; the TMA unit writes it through the async proxy
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive_expect_tx(bar, (uint32_t)(AX::LAYERS * EP * EQ * 4));
+        const CUtensorMap* map = p.maps + ((A * ST_MENU + mP) * ST_MENU + mQ);
+        const uint32_t dst = smem_u32(ring + (size_t)slot * ST_STAGE_FLOATS);
+        // tensor coordinates are (axis 2, axis 1, axis 0)
+        int c[3];
+        c[2 - A] = first;
+        c[2 - AX::P] = loP;
+        c[2 - AX::Q] = loQ;
+        tma_load_3d(dst, map, c[0], c[1], c[2], bar);
+      } else {
+        mbar_arrive(bar);
+      }
+      __threadfence_block();
+      *(volatile int*)&sh.issued = t;
+    }
+    __syncwarp();
+  }
+  // every load this warp issued must have landed before the CTA may retire (its shared memory is re-used)
+  for (int q = max(0, issued - ST_R); q < issued; ++q) {
+    const uint32_t bar = full0 + 8u * (uint32_t)(q % ST_R);
+    const uint32_t parity = (uint32_t)(q / ST_R) & 1u;
+    bool done = false;
+    for (int spin = 0; spin < (1 << 22) && !done; ++spin) done = mbar_try_wait(bar, parity);
+  }
+}
+
+template <bool JAC>
+__global__ void __launch_bounds__(ST_NC + 32, XVR_ST_MIN_CTAS) trilinear_fwd_staged_kernel(const __grid_constant__ StagedParams p) {
+  extern __shared__ __align__(128) float ring_raw[];  // ST_R * ST_STAGE_FLOATS floats (+ 128 bytes of slack)
+  __shared__ CtaShared sh;
+  float* ring = reinterpret_cast<float*>(((uintptr_t)ring_raw + 127) & ~(uintptr_t)127);  // TMA destinations: 128 B
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool producer = warp == ST_NW;
   const int tiles = p.tiles_x * p.tiles_y;
   const int b = blockIdx.x / tiles;
   const int tile = blockIdx.x - b * tiles;
   const int ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
-  const int i0 = ty * ST_T, j0 = tx * ST_T;
-  const int pi = i0 + (lane & 15), pj = j0 + warp * 2 + (lane >> 4);
-  const bool inside = pi < p.H && pj < p.W;
+  const int i0 = ty * ST_TI, j0 = tx * ST_TJ;
+  const int pi = i0 + (lane & (ST_TI - 1)), pj = j0 + warp * ST_CPW + (lane / ST_TI);
+  const bool inside = !producer && pi < p.H && pj < p.W;
   const int N = p.H * p.W;
   const int n = inside ? pi * p.W + pj : 0;
   const int np = p.n_points;
-  const int size[3] = {p.vol.D0, p.vol.D1, p.vol.D2};
-  const uint32_t bar = smem_u32(&mbar_storage[0]);  // the second barrier sits 8 bytes further
 
   if (tid == 0) {
-    mbar_init(bar, 256);
-    mbar_init(bar + 8u, 256);
+    for (int r = 0; r < ST_R; ++r) mbar_init(smem_u32(&sh.full[r]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    t_first = INT_MAX;
-    t_last = INT_MIN;
+    sh.t_first = INT_MAX;
+    sh.t_last = INT_MIN;
+    sh.broken = 0;
   }
 
   // ---- this thread's ray, exactly as trilinear_fwd_kernel sets it up
   float s[3], d[3], L;
   generate_ray(p.geom, b, n, p.eps, s, d, L);
   const float lo0[3] = {0.f, 0.f, 0.f};
-  const float hi0[3] = {(float)(size[0] - 1), (float)(size[1] - 1), (float)(size[2] - 1)};
+  const float hi0[3] = {(float)(p.vol.D0 - 1), (float)(p.vol.D1 - 1), (float)(p.vol.D2 - 1)};
   const AlphaRange ar = alpha_range(s, d, lo0, hi0);
   const float span = ar.amax - ar.amin;
   const float w = st_step_weight(p.step_mode, span, np);
   bool live = inside;
   if (live) {  // rays that never come within one voxel of the volume are an exact 0
     const float plo[3] = {-1.f, -1.f, -1.f};
-    const float phi[3] = {(float)size[0], (float)size[1], (float)size[2]};
+    const float phi[3] = {(float)p.vol.D0, (float)p.vol.D1, (float)p.vol.D2};
     const AlphaRange pr = alpha_range(s, d, plo, phi);
     live = pr.amin < pr.amax;
   }
@@ -151,248 +491,70 @@ __global__ void __launch_bounds__(256, STAGES == 1 ? XVR_ST_MIN_CTAS : 2) trilin
   bool forward;
   {
     float cs[3], cd[3], cl;
-    generate_ray(p.geom, b, min(i0 + ST_T / 2, p.H - 1) * p.W + min(j0 + ST_T / 2, p.W - 1), p.eps, cs, cd, cl);
+    generate_ray(p.geom, b, min(i0 + ST_TI / 2, p.H - 1) * p.W + min(j0 + ST_TJ / 2, p.W - 1), p.eps, cs, cd, cl);
     A = fabsf(cd[1]) > fabsf(cd[0]) ? 1 : 0;
-    if (fabsf(cd[2]) > fabsf(pick3(cd, A))) A = 2;
-    forward = pick3(cd, A) > 0.f;
+    if (fabsf(cd[2]) > fabsf(A == 1 ? cd[1] : cd[0])) A = 2;
+    forward = (A == 0 ? cd[0] : (A == 1 ? cd[1] : cd[2])) > 0.f;
   }
-  const int O1 = A == 0 ? 1 : 0, O2 = A == 2 ? 1 : 2;  // the other two axes, ascending
+  const float sA = A == 0 ? s[0] : (A == 1 ? s[1] : s[2]), dA = A == 0 ? d[0] : (A == 1 ? d[1] : d[2]);
+  const int size_a = A == 0 ? p.vol.D0 : (A == 1 ? p.vol.D1 : p.vol.D2);
 
-  // ---- corner rays of the tile, held by lanes 0..3 (and 4..7) of warp 0 for the per-slab box
-  float qs[3] = {0.f, 0.f, 0.f}, qd[3] = {1.f, 1.f, 1.f};
-  if (warp == 0 && lane < 8) {
-    const int ci = (lane & 1) ? min(i0 + ST_T - 1, p.H - 1) : i0;
-    const int cj = (lane & 2) ? min(j0 + ST_T - 1, p.W - 1) : j0;
-    float ql;
-    generate_ray(p.geom, b, ci * p.W + cj, p.eps, qs, qd, ql);
-  }
-  const float qsA = pick3(qs, A), qdA = pick3(qd, A), qs1 = pick3(qs, O1), qd1 = pick3(qd, O1), qs2 = pick3(qs, O2),
-              qd2 = pick3(qd, O2);
-  const float sA = pick3(s, A), dA = pick3(d, A);
-
-  const float lstep = 1.0f / (float)(np - 1);
   float sumV = 0.f;
   float Aj[3] = {0.f, 0.f, 0.f}, Uj[3] = {0.f, 0.f, 0.f};
   unsigned n_shared = 0, n_global = 0, n_timeout = 0;
-
-  auto accumulate = [&](float u, float v, const float g[3]) {
-    sumV += v;
-    if (JAC) {
-#pragma unroll
-      for (int a = 0; a < 3; ++a) {
-        Aj[a] += g[a];
-        Uj[a] = fmaf(u, g[a], Uj[a]);
-      }
-    }
-  };
 
   // A ray is "regular" when it advances along A in the frustum's direction; anything else (a ray that only grazes
   // the zero padding and is marched with a negative span, a ray running the other way) is marched here and now
   // from global memory, samples in the same order.
   const bool regular = live && span > 0.f && dA != 0.f && ((dA > 0.f) == forward);
   if (live && !regular) {
+    const float lstep = 1.0f / (float)(np - 1);
     for (int k = 0; k < np; ++k) {
       const float u = linspace01(k, np, lstep);
       const float alpha = fmaf(u, span, ar.amin);
       float g[3];
       const float v = sample_trilinear<JAC, false>(p.vol, fmaf(alpha, d[0], s[0]), fmaf(alpha, d[1], s[1]),
                                                    fmaf(alpha, d[2], s[2]), g);
-      accumulate(u, v, g);
+      sumV += v;
+      if (JAC) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          Aj[a] += g[a];
+          Uj[a] = fmaf(u, g[a], Uj[a]);
+        }
+      }
     }
     n_global += np;
+#ifdef XVR_ST_DEBUG
+    if (p.stats) atomicAdd(p.stats + 4, (unsigned long long)np);  // irregular rays
+#endif
   }
 
-  __syncthreads();  // barrier initialised, t_first / t_last reset
+  __syncthreads();  // barriers initialised, t_first / t_last reset
   if (regular) {
     const float a_end = fmaf(1.0f, span, ar.amin);
     const int c0 = (int)floorf(fmaf(ar.amin, dA, sA)), c1 = (int)floorf(fmaf(a_end, dA, sA));
-    const int sa = slab_of(c0), sb = slab_of(c1);
-    atomicMin(&t_first, forward ? sa : -sa);
-    atomicMax(&t_last, forward ? sb : -sb);
+    const int off = forward ? ST_K : size_a + ST_K - 1;
+    const int sgn = forward ? 1 : -1;
+    atomicMin(&sh.t_first, (off + sgn * c0) >> ST_KLOG);
+    atomicMax(&sh.t_last, (off + sgn * c1) >> ST_KLOG);
   }
+  if (!producer && lane == 0) sh.progress[warp] = INT_MIN;  // set below once t_first is known
   __syncthreads();
-  const int tf = t_first, tl = t_last;  // travel index t = +-slab number, increasing along the rays
+  const int tf = sh.t_first, tl = sh.t_last;
+  if (!producer && lane == 0) sh.progress[warp] = tf;
+  if (tid == 0) sh.issued = tf - 1;
+  __syncthreads();  // the last CTA-wide barrier: from here on producer and consumers only meet through the ring
 
-  // next sample of this ray: index k, and (once computed) its position
-  int k = 0;
-  bool have = false;
-  float cu = 0.f, cx = 0.f, cy = 0.f, cz = 0.f;
-  int ct = 0;
-  bool broken = false;  // a barrier wait timed out: this thread stops trusting the staging buffers
-
-  // ---- 1. box of slab t (warp 0; lanes 0-3: corner rays at plane loA, lanes 4-7: at plane loA + ST_K)
-  auto publish_box = [&](int t, BoxDesc& desc) {
-    const int slab = forward ? t : -t;
-    const int loA = (slab - 1) * ST_K;
-    float v1 = 0.f, v2 = 0.f;
-    bool ok = true;
-    if (lane < 8) {
-      const float plane = (float)(loA + ((lane & 4) ? ST_K : 0));
-      ok = fabsf(qdA) > 1e-12f;
-      const float al = ok ? (plane - qsA) / qdA : 0.f;
-      v1 = fmaf(al, qd1, qs1);
-      v2 = fmaf(al, qd2, qs2);
-      ok = ok && fabsf(v1) < 1e8f && fabsf(v2) < 1e8f;
-    }
-    float mn1 = lane < 8 ? v1 : INFINITY, mx1 = lane < 8 ? v1 : -INFINITY;
-    float mn2 = lane < 8 ? v2 : INFINITY, mx2 = lane < 8 ? v2 : -INFINITY;
-    const unsigned bad = __ballot_sync(0xffffffffu, !ok);
-#pragma unroll
-    for (int o = 4; o > 0; o >>= 1) {
-      mn1 = fminf(mn1, __shfl_xor_sync(0xffffffffu, mn1, o));
-      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, o));
-      mn2 = fminf(mn2, __shfl_xor_sync(0xffffffffu, mn2, o));
-      mx2 = fmaxf(mx2, __shfl_xor_sync(0xffffffffu, mx2, o));
-    }
-    if (lane == 0) {
-      // cells loA .. loA+K-1 need layers loA .. loA+K; on the other axes one cell of margin each side (the
-      // per-sample positions are rounded differently from this bound) plus the upper corner
-      const int l1 = (int)floorf(mn1) - 1, h1 = (int)floorf(mx1) + 2;
-      const int l2 = (int)floorf(mn2) - 1, h2 = (int)floorf(mx2) + 2;
-      int lo[3], hi[3];
-#pragma unroll
-      for (int a = 0; a < 3; ++a) {  // nothing beyond one layer of zero padding is ever read
-        lo[a] = max(a == A ? loA : (a == O1 ? l1 : l2), -1);
-        hi[a] = min(a == A ? loA + ST_K : (a == O1 ? h1 : h2), size[a]);
-      }
-      lo[2] &= ~3;  // 16-byte rows (two's complement: -1 -> -4)
-      hi[2] = ((hi[2] + 4) & ~3) - 1;
-      long long elems = 1;
-#pragma unroll
-      for (int a = 0; a < 3; ++a) {
-        desc.lo[a] = lo[a];
-        desc.E[a] = hi[a] - lo[a] + 1;
-        elems *= (long long)max(desc.E[a], 0);
-      }
-      desc.staged = bad == 0 && elems > 0 && elems <= ST_CAP && (size[2] & 3) == 0 && ((size_t)p.vol.data & 15) == 0;
-    }
-  };
-
-  // ---- 2. stage a box: one bulk copy per row that intersects the volume, zeros elsewhere.  Called by every thread
-  // (CTA-uniform on desc.staged): every thread arrives at `bar_addr` exactly once per staged box.
-  auto stage_box = [&](const BoxDesc& desc, float* buf, uint32_t bar_addr) {
-    if (desc.staged == 0) return;
-    if (broken) {
-      mbar_arrive(bar_addr);
-      return;
-    }
-    // the buffer was read (and its padding written) through the generic proxy; the bulk copies write it through the
-    // async proxy
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    const int bl0 = desc.lo[0], bl1 = desc.lo[1], bl2 = desc.lo[2];
-    const int E0 = desc.E[0], E1 = desc.E[1], E2 = desc.E[2];
-    const int rows = E0 * E1;
-    const int c_lo = max(bl2, 0), c_hi = min(bl2 + E2, size[2]);  // multiples of 4
-    uint32_t bytes = 0;
-    for (int r = tid; r < rows; r += 256) {
-      const int g0 = bl0 + r / E1, g1 = bl1 + r % E1;
-      if ((unsigned)g0 < (unsigned)size[0] && (unsigned)g1 < (unsigned)size[1] && c_hi > c_lo)
-        bytes += (uint32_t)(c_hi - c_lo) * 4u;
-    }
-    if (bytes) mbar_arrive_expect_tx(bar_addr, bytes); else mbar_arrive(bar_addr);
-    for (int r = tid; r < rows; r += 256) {
-      const int g0 = bl0 + r / E1, g1 = bl1 + r % E1;
-      float* row = buf + (size_t)r * E2;
-      const bool in = (unsigned)g0 < (unsigned)size[0] && (unsigned)g1 < (unsigned)size[1] && c_hi > c_lo;
-      const int z_lo = in ? c_lo - bl2 : E2, z_hi = in ? c_hi - bl2 : E2;  // [z_lo, z_hi) comes from the volume
-      for (int c = 0; c < z_lo; ++c) row[c] = 0.f;
-      for (int c = z_hi; c < E2; ++c) row[c] = 0.f;
-      if (in)
-        bulk_g2s(smem_u32(row + z_lo), p.vol.data + ((int64_t)g0 * p.vol.s0 + (int64_t)g1 * p.vol.s1 + c_lo),
-                 (uint32_t)(c_hi - c_lo) * 4u, bar_addr);
-    }
-  };
-
-  // bounded wait for the bulk copies of a staged box; false (and `broken`) when the barrier does not complete
-  auto wait_box = [&](uint32_t bar_addr, uint32_t parity) -> bool {
-    if (broken) return false;
-    bool done = false;
-    for (int spin = 0; spin < (1 << 16) && !done; ++spin) done = mbar_try_wait(bar_addr, parity);
-    if (!done) {
-      broken = true;
-      ++n_timeout;
-    }
-    return done;
-  };
-
-  // ---- 3. this ray's samples whose cell lies in slab t, from `buf` when `staged`
-  auto march_slab = [&](int t, const BoxDesc& desc, const float* buf, bool staged) {
-    if (!regular) return;
-    const int bl0 = desc.lo[0], bl1 = desc.lo[1], bl2 = desc.lo[2];
-    const int E0 = desc.E[0], E1 = desc.E[1], E2 = desc.E[2];
-    while (k < np) {
-      if (!have) {
-        cu = linspace01(k, np, lstep);
-        const float alpha = fmaf(cu, span, ar.amin);
-        cx = fmaf(alpha, d[0], s[0]);
-        cy = fmaf(alpha, d[1], s[1]);
-        cz = fmaf(alpha, d[2], s[2]);
-        const float pa = A == 0 ? cx : (A == 1 ? cy : cz);
-        const int cs = slab_of((int)floorf(pa));
-        ct = forward ? cs : -cs;
-        have = true;
-      }
-      if (ct > t) break;  // belongs to a later slab
-      float g[3], v;
-      const float fx0 = floorf(cx), fy0 = floorf(cy), fz0 = floorf(cz);
-      const int lx = (int)fx0 - bl0, ly = (int)fy0 - bl1, lz = (int)fz0 - bl2;
-      if (staged && ct == t && (unsigned)lx < (unsigned)(E0 - 1) && (unsigned)ly < (unsigned)(E1 - 1) &&
-          (unsigned)lz < (unsigned)(E2 - 1)) {
-        const float* q = buf + ((size_t)lx * E1 + ly) * E2 + lz;
-        const int sy = E2, sx = E1 * E2;
-        v = trilinear_interp<JAC>(q[0], q[1], q[sy], q[sy + 1], q[sx], q[sx + 1], q[sx + sy], q[sx + sy + 1],
-                                  cx - fx0, cy - fy0, cz - fz0, g);
-        ++n_shared;
-      } else {
-        v = sample_trilinear<JAC, false>(p.vol, cx, cy, cz, g);
-        ++n_global;
-      }
-      accumulate(cu, v, g);
-      have = false;
-      ++k;
-    }
-  };
-
-  if (STAGES == 1) {
-    // One buffer: publish -> barrier -> stage -> barrier + wait -> march.  Box descriptors are double-buffered so
-    // that warp 0 can publish slab t+1 while slower warps still copy slab t's descriptor into registers.
-    uint32_t phase = 0;
-    for (int t = tf; t <= tl; ++t) {
-      BoxDesc& desc = descs[(t - tf) & 1];
-      if (warp == 0) publish_box(t, desc);
-      __syncthreads();  // everyone is done with the previous slab's buffer; the new box is published
-      bool staged = desc.staged != 0;
-      if (staged) {  // CTA-uniform
-        stage_box(desc, box, bar);
-        __syncthreads();  // the zero fills are visible
-        staged = wait_box(bar, phase & 1u);
-        ++phase;
-      }
-      march_slab(t, desc, box, staged);
-    }
-  } else {
-    // Two buffers: while slab t is marched from buffer t&1, the bulk copies of slab t+1 fill buffer (t+1)&1.  One
-    // barrier per slab.  Descriptors live in three slots: slot (t+1)%3 is rewritten while slab t-1's readers are
-    // still possible only for slots (t-1)%3 and t%3.
-    uint32_t uses0 = 0u, uses1 = 0u;  // completed phases of each barrier
-    if (tf <= tl) {
-      if (warp == 0) publish_box(tf, descs[0]);
-      __syncthreads();
-      stage_box(descs[0], box, bar);
-    }
-    for (int t = tf; t <= tl; ++t) {
-      const int i = t - tf;
-      BoxDesc& desc = descs[i % 3];
-      BoxDesc& next = descs[(i + 1) % 3];
-      if (t < tl && warp == 0) publish_box(t + 1, next);
-      __syncthreads();  // slab t-1 fully marched (its buffer is free), slab t's zero fills and the next box visible
-      if (t < tl) stage_box(next, box + (size_t)((i + 1) & 1) * ST_CAP, bar + 8u * (uint32_t)((i + 1) & 1));
-      bool staged = desc.staged != 0;
-      if (staged) {
-        staged = wait_box(bar + 8u * (uint32_t)(i & 1), ((i & 1) ? uses1 : uses0) & 1u);
-        if (i & 1) ++uses1; else ++uses0;
-      }
-      march_slab(t, desc, box + (size_t)(i & 1) * ST_CAP, staged);
+  if (tf <= tl) {
+    if (producer) {
+      if (A == 0) producer_loop<0>(p, sh, ring, tf, tl, forward, b, i0, j0);
+      else if (A == 1) producer_loop<1>(p, sh, ring, tf, tl, forward, b, i0, j0);
+      else producer_loop<2>(p, sh, ring, tf, tl, forward, b, i0, j0);
+    } else {
+      if (A == 0) consumer_march<0, JAC>(p, sh, ring, tf, forward, regular, s, d, ar.amin, span, warp, sumV, Aj, Uj, n_shared, n_global, n_timeout);
+      else if (A == 1) consumer_march<1, JAC>(p, sh, ring, tf, forward, regular, s, d, ar.amin, span, warp, sumV, Aj, Uj, n_shared, n_global, n_timeout);
+      else consumer_march<2, JAC>(p, sh, ring, tf, forward, regular, s, d, ar.amin, span, warp, sumV, Aj, Uj, n_shared, n_global, n_timeout);
     }
   }
 
@@ -441,28 +603,123 @@ __global__ void __launch_bounds__(256, STAGES == 1 ? XVR_ST_MIN_CTAS : 2) trilin
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Tensor maps: one per (marching axis, box extent on the first lateral axis, on the second), in device memory,
+// built once per (volume pointer, shape) and cached.  cuTensorMapEncodeTiled comes from the driver through the
+// runtime's entry-point query, so the library does not link against libcuda.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct MapKey {
+  const void* ptr;
+  int D0, D1, D2, device;
+  bool operator==(const MapKey& o) const {
+    return ptr == o.ptr && D0 == o.D0 && D1 == o.D1 && D2 == o.D2 && device == o.device;
+  }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    return std::hash<const void*>()(k.ptr) ^ ((size_t)k.D0 * 1000003u) ^ ((size_t)k.D1 * 10007u) ^ (size_t)k.D2 ^
+           ((size_t)k.device << 20);
+  }
+};
+static std::mutex g_map_mutex;
+static std::unordered_map<MapKey, CUtensorMap*, MapKeyHash> g_maps;  // device arrays of 3 * ST_MENU^2 maps
+
+static const CUtensorMap* tensor_maps(const float* volume, int D0, int D1, int D2, cudaStream_t st) {
+  int device = 0;
+  cudaGetDevice(&device);
+  const MapKey key = {volume, D0, D1, D2, device};
+  std::lock_guard<std::mutex> lock(g_map_mutex);
+  auto it = g_maps.find(key);
+  if (it != g_maps.end()) return it->second;
+  static EncodeTiledFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
+      set_last_error("xvr_trilinear_drr_fwd_staged: cuTensorMapEncodeTiled is not available from this driver");
+      return nullptr;
+    }
+    encode = (EncodeTiledFn)fn;
+  }
+  const int count = 3 * ST_MENU * ST_MENU;
+  CUtensorMap* host = new CUtensorMap[count];
+  const cuuint64_t dims[3] = {(cuuint64_t)D2, (cuuint64_t)D1, (cuuint64_t)D0};
+  const cuuint64_t strides[2] = {(cuuint64_t)D2 * 4, (cuuint64_t)D1 * D2 * 4};
+  const cuuint32_t ones[3] = {1, 1, 1};
+  for (int A = 0; A < 3; ++A)
+    for (int mP = 0; mP < ST_MENU; ++mP)
+      for (int mQ = 0; mQ < ST_MENU; ++mQ) {
+        const cuuint32_t EP = ST_EMIN + ESTEP * mP, EQ = ST_EMIN + ESTEP * mQ;
+        cuuint32_t box[3];  // (axis 2, axis 1, axis 0) extents; lateral axes P < Q
+        if (A == 0) { box[0] = EQ; box[1] = EP; box[2] = ST_L; }       // P = axis 1, Q = axis 2
+        else if (A == 1) { box[0] = EQ; box[1] = ST_L; box[2] = EP; }  // P = axis 0, Q = axis 2
+        else { box[0] = ST_L; box[1] = EQ; box[2] = EP; }              // P = axis 0, Q = axis 1
+        // a box that does not fit the stage is never requested; encode a minimal legal one in its place
+        if (A == 2) box[0] = ST_LP;  // the inner extent is 16-byte granular: 5 layers -> 8
+        // a box that does not fit the stage is never requested; encode a minimal legal one in its place
+        if ((A == 2 ? ST_LP : ST_L) * EP * EQ > (cuuint32_t)ST_STAGE_FLOATS) { box[0] = A == 2 ? 4 : 16; box[1] = 1; box[2] = 1; }
+        CUresult r = encode(&host[(A * ST_MENU + mP) * ST_MENU + mQ], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)volume,
+                            dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+          char msg[160];
+          snprintf(msg, sizeof(msg), "xvr_trilinear_drr_fwd_staged: cuTensorMapEncodeTiled failed (%d) for axis %d box %u x %u",
+                   (int)r, A, EP, EQ);
+          set_last_error(msg);
+          delete[] host;
+          return nullptr;
+        }
+      }
+  CUtensorMap* dev = nullptr;
+  if (cudaMalloc(&dev, sizeof(CUtensorMap) * count) != cudaSuccess ||
+      cudaMemcpy(dev, host, sizeof(CUtensorMap) * count, cudaMemcpyHostToDevice) != cudaSuccess) {
+    set_last_error("xvr_trilinear_drr_fwd_staged: could not upload the tensor maps");
+    delete[] host;
+    cudaGetLastError();
+    return nullptr;
+  }
+  delete[] host;
+  if (g_maps.size() >= 64) {  // volumes come and go (training subjects): keep the table bounded
+    for (auto& kv : g_maps) cudaFree(kv.second);
+    g_maps.clear();
+  }
+  g_maps[key] = dev;
+  (void)st;
+  return dev;
+}
+
 }  // namespace xvr
 
 using namespace xvr;
 
-// Same arguments as xvr_trilinear_drr_fwd without the texture handle and tile shape, plus `stages` (1: one staging
-// buffer, three CTAs per SM; 2: double-buffered, the copies of slab t+1 overlap the march of slab t, two CTAs per
-// SM) and an optional device counter triple `stats` = {samples served from shared memory, from global memory,
-// barrier time-outs} the caller zeroes.
+// Same arguments as xvr_trilinear_drr_fwd without the texture handle and tile shape, plus an optional device counter
+// triple `stats` = {samples served from shared memory, from global memory, barrier time-outs} the caller zeroes.
+// Needs a 16-byte aligned volume whose contiguous extent is a multiple of 4 (the TMA unit's stride granularity);
+// other volumes are an invalid argument here and go through xvr_trilinear_drr_fwd.
 extern "C" int xvr_trilinear_drr_fwd_staged(const float* volume, int D0, int D1, int D2, const float* cam2vox,
                                             const float* cam2world, const float* det9, int B, int det_h, int det_w,
-                                            int n_points, int step_mode, float eps, int stages, float* out, float* jac,
+                                            int n_points, int step_mode, float eps, float* out, float* jac,
                                             unsigned long long* stats, void* stream) {
   if (!volume || !cam2vox || !cam2world || !det9 || !out || B <= 0 || det_h <= 0 || det_w <= 0 || D0 < 2 || D1 < 2 ||
-      D2 < 2 || n_points < 2 || step_mode < 0 || step_mode > 2 || (stages != 1 && stages != 2)) {
+      D2 < 2 || n_points < 2 || step_mode < 0 || step_mode > 2) {
     set_last_error("xvr_trilinear_drr_fwd_staged: invalid argument");
+    return XVR_ERR_INVALID;
+  }
+  if (((size_t)volume & 15) != 0 || (D2 & 3) != 0) {
+    set_last_error("xvr_trilinear_drr_fwd_staged: the TMA unit needs a 16-byte aligned volume with D2 % 4 == 0");
     return XVR_ERR_INVALID;
   }
   if ((int64_t)D0 * D1 * D2 >= (int64_t)1 << 31) {
     set_last_error("xvr_trilinear_drr_fwd_staged: volume too large for 32-bit voxel offsets");
     return XVR_ERR_INVALID;
   }
+  cudaStream_t st = (cudaStream_t)stream;
   StagedParams p = {};
+  p.maps = tensor_maps(volume, D0, D1, D2, st);
+  if (!p.maps) return XVR_ERR_CUDA;
   p.vol.data = volume;
   p.vol.D0 = D0;
   p.vol.D1 = D1;
@@ -484,8 +741,8 @@ extern "C" int xvr_trilinear_drr_fwd_staged(const float* volume, int D0, int D1,
   p.n_points = n_points;
   p.step_mode = step_mode;
   p.eps = eps;
-  p.tiles_x = (det_w + ST_T - 1) / ST_T;
-  p.tiles_y = (det_h + ST_T - 1) / ST_T;
+  p.tiles_x = (det_w + ST_TJ - 1) / ST_TJ;
+  p.tiles_y = (det_h + ST_TI - 1) / ST_TI;
   p.out = out;
   p.jac = jac;
   p.stats = stats;
@@ -494,16 +751,11 @@ extern "C" int xvr_trilinear_drr_fwd_staged(const float* volume, int D0, int D1,
     set_last_error("xvr_trilinear_drr_fwd_staged: grid too large");
     return XVR_ERR_INVALID;
   }
-  const int smem = stages * ST_CAP * (int)sizeof(float);
-  cudaStream_t st = (cudaStream_t)stream;
+  const int smem = ST_R * ST_STAGE_FLOATS * (int)sizeof(float) + 128;
   auto launch = [&](auto kernel) {
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    kernel<<<(unsigned)grid, 256, smem, st>>>(p);
+    kernel<<<(unsigned)grid, ST_NC + 32, smem, st>>>(p);
   };
-  if (stages == 1) {
-    if (jac) launch(trilinear_fwd_staged_kernel<true, 1>); else launch(trilinear_fwd_staged_kernel<false, 1>);
-  } else {
-    if (jac) launch(trilinear_fwd_staged_kernel<true, 2>); else launch(trilinear_fwd_staged_kernel<false, 2>);
-  }
+  if (jac) launch(trilinear_fwd_staged_kernel<true>); else launch(trilinear_fwd_staged_kernel<false>);
   return check_launch("xvr_trilinear_drr_fwd_staged");
 }

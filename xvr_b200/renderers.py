@@ -143,40 +143,46 @@ class _RenderRays(torch.autograd.Function):
     def forward(ctx, volume, source, target, raylen, labels, C, kind, args, det_hw, voltex):
         source, target, raylen = cuda_f32(source, "source"), cuda_f32(target, "target"), cuda_f32(raylen, "raylen")
         B, N = _check_rays(volume, source, target, raylen)
-        if ctx.needs_input_grad[0]:
-            raise _lib.XvrB200Error("d/dvolume is computed by xvr_b200.renderers.volume_gradient, not by autograd")
         lw, cw = _tile_shape()
         det_h, det_w = det_hw if det_hw is not None and det_hw[0] * det_hw[1] == N else (0, 0)
         need_pose_grad = any(ctx.needs_input_grad[1:4])
+        need_vol_grad = ctx.needs_input_grad[0]
         out = torch.empty(B, C, N, device=volume.device, dtype=torch.float32)
         ctx.empty = B == 0 or N == 0
         if ctx.empty:  # empty in -> empty out, as grid_sample does; nothing to launch
             return out
         # with label channels the Jacobian is the one of the channel SUM: enough whenever the caller collapses the
         # channels (trainer.py:294 img.sum(dim=1)); backward() falls back to the recompute kernel otherwise
-        jac = torch.empty(B, 7, N, device=volume.device, dtype=torch.float32) if need_pose_grad else None
+        jac = (torch.empty(B, 7, N, device=volume.device, dtype=torch.float32)
+               if need_pose_grad and not need_vol_grad else None)  # d/dvolume re-marches anyway: no Jacobian to keep
         vol_args = (ptr(volume),) if voltex is False else (ptr(volume), voltex)
         ctx.common = (*vol_args, *volume.shape, ptr(labels), C, ptr(source), ptr(target), ptr(raylen), B, N, *args,
                       det_h, det_w, lw, cw)
         call(f"xvr_{kind}_rays_fwd", *ctx.common, ptr(out), ptr(jac), _lib.opts_word(), stream())
-        ctx.kind = kind
-        if need_pose_grad:
-            # the recompute path (per-channel upstream gradients) needs the inputs; saving them keeps the raw
-            # pointers of ctx.common alive
-            ctx.save_for_backward(jac, *((volume, source, target, raylen, labels) if labels is not None else ()))
+        ctx.kind, ctx.C, ctx.shape = kind, C, tuple(volume.shape)
+        if need_pose_grad or need_vol_grad:
+            # the recompute path (per-channel upstream gradients, d/dvolume) needs the inputs; saving them keeps the
+            # raw pointers of ctx.common alive
+            keep = labels is not None or need_vol_grad
+            ctx.save_for_backward(jac, *((volume, source, target, raylen, labels) if keep else ()))
         return out
 
     @staticmethod
     def backward(ctx, gout):
-        gout_shared = gout.shape[1] == 1 or gout.stride(1) == 0
+        need_vol_grad = ctx.needs_input_grad[0]
+        gout_shared = (gout.shape[1] == 1 or gout.stride(1) == 0) and not need_vol_grad
         gout = cuda_f32(gout[:, :1] if gout_shared else gout, "grad_output")
         B, _, N = gout.shape
         dev = gout.device
         gsource = torch.empty(B, 1, 3, device=dev, dtype=torch.float32)
         gtarget = torch.empty(B, N, 3, device=dev, dtype=torch.float32)
         graylen = torch.empty(B, 1, N, device=dev, dtype=torch.float32)
+        # d/dvolume from the ray entry point: the reference's own formulation (one RED.ADD per corner / segment into a
+        # zeroed volume, non-deterministic summation order) -- rays given as tensors carry no detector geometry to
+        # derive an atomics-free ownership from; DRR.forward's fused path has one (csrc/volgrad.cu, siddon_volgrad.cu)
+        gvol = torch.zeros(ctx.shape, device=dev, dtype=torch.float32) if need_vol_grad else None
         if ctx.empty:
-            return None, gsource.zero_(), gtarget, graylen, None, None, None, None, None, None
+            return gvol, gsource.zero_(), gtarget, graylen, None, None, None, None, None, None
         work = torch.empty(B, 3, N, device=dev, dtype=torch.float32)
         jac = ctx.saved_tensors[0]
         # One upstream gradient per ray: single channel, or every channel sees the same gradient -- autograd hands
@@ -186,8 +192,8 @@ class _RenderRays(torch.autograd.Function):
                  ptr(work), stream())
         else:
             call(f"xvr_{ctx.kind}_rays_bwd", *ctx.common, ptr(gout), ptr(gsource), ptr(gtarget), ptr(graylen),
-                 ptr(work), *((_lib.opts_word(),) if ctx.kind == "siddon" else ()), stream())
-        return None, gsource, gtarget, graylen, None, None, None, None, None, None
+                 ptr(work), ptr(gvol), *((_lib.opts_word(),) if ctx.kind == "siddon" else ()), stream())
+        return gvol, gsource, gtarget, graylen, None, None, None, None, None, None
 
 
 # Diagnostics of the staged variant: set _staged_stats["tensor"] to a zeroed int64 CUDA tensor of 3 elements to collect
@@ -203,9 +209,6 @@ class _RenderDRR(torch.autograd.Function):
     @staticmethod
     def forward(ctx, volume, cam2vox, cam2world, det9, det_hw, kind, args, voltex):
         cam2vox, cam2world = cuda_f32(cam2vox, "cam2vox"), cuda_f32(cam2world, "cam2world")
-        if kind == "siddon" and ctx.needs_input_grad[0]:
-            raise _lib.XvrB200Error("d/dvolume of the Siddon renderer goes through the ray entry point "
-                                    "(drr.renderer(volume, source, target, raylen))")
         B = cam2vox.shape[0]
         H, W = det_hw
         lw, cw = _tile_shape()
@@ -220,15 +223,15 @@ class _RenderDRR(torch.autograd.Function):
         if kind == "siddon":
             call("xvr_siddon_drr_fwd", ptr(volume), *volume.shape, ptr(cam2vox), ptr(cam2world), det, B, H, W, *args,
                  lw, cw, ptr(out), ptr(jac), _lib.opts_word(), stream())
-        elif staged in ("1", "2"):
-            # opt-in, not yet run on a GPU: bricks staged in shared memory by TMA bulk copies, single (1) or double
-            # (2) buffered (csrc/trilinear_staged.cu)
+        elif staged == "1" and volume.shape[2] % 4 == 0 and volume.data_ptr() % 16 == 0:
+            # bricks staged in shared memory by the TMA unit (csrc/trilinear_staged.cu)
             call("xvr_trilinear_drr_fwd_staged", ptr(volume), *volume.shape, ptr(cam2vox), ptr(cam2world), det, B, H, W,
-                 *args, int(staged), ptr(out), ptr(jac), ptr(_staged_stats.get("tensor")), stream())
+                 *args, ptr(out), ptr(jac), ptr(_staged_stats.get("tensor")), stream())
         else:
             call("xvr_trilinear_drr_fwd", ptr(volume), voltex, *volume.shape, ptr(cam2vox), ptr(cam2world), det, B, H,
                  W, *args, lw, cw, ptr(out), ptr(jac), _lib.opts_word(), stream())
         ctx.det = (det, B, H, W, args, tuple(volume.shape))
+        ctx.kind = kind
         ctx.save_for_backward(jac, *((cam2vox, cam2world) if ctx.needs_input_grad[0] else ()))
         return out
 
@@ -253,10 +256,14 @@ class _RenderDRR(torch.autograd.Function):
             full[:, :3] = cam2vox
             full[:, 3, 3] = 1.0
             vox2cam = torch.linalg.inv(full)[:, :3].to(torch.float32).contiguous()
-            work = torch.empty(B * H * W * 12, device=gout.device, dtype=torch.float32)
             gvol = torch.empty(shape, device=gout.device, dtype=torch.float32)
-            call("xvr_trilinear_drr_bwd_volume", ptr(cam2vox), ptr(vox2cam), ptr(cam2world), det, B, H, W, *args,
-                 ptr(gout), *shape, ptr(work), ptr(gvol), 0, _lib.opts_word(), stream())
+            if ctx.kind == "siddon":
+                call("xvr_siddon_drr_bwd_volume", ptr(cam2vox), ptr(vox2cam), ptr(cam2world), det, B, H, W, *args,
+                     ptr(gout), *shape, ptr(gvol), 0, _lib.opts_word(), stream())
+            else:
+                work = torch.empty(B * H * W * 12, device=gout.device, dtype=torch.float32)
+                call("xvr_trilinear_drr_bwd_volume", ptr(cam2vox), ptr(vox2cam), ptr(cam2world), det, B, H, W, *args,
+                     ptr(gout), *shape, ptr(work), ptr(gvol), 0, _lib.opts_word(), stream())
         return gvol, gG, None, None, None, None, None, None
 
 
