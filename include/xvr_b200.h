@@ -210,6 +210,13 @@ int xvr_hu_to_density(const float* hu, long long n, float air, float bone, float
                       const float* multiplier_dev /* NULL, or DEVICE float overriding `multiplier` */,
                       const float* stats, float* out, void* stream);
 
+/* ---- The post-render epilogue of the training iteration (/root/reference/src/xvr/model/trainer.py:292-302 +
+ * utils/preprocess.py:28-29) in one launch: img (B,C,N) -> sum_img (B,N) = img.sum(dim=1) (NULL allowed when C == 1),
+ * stats (B,4) = {foreground fraction, keep (0/1: fraction > img_threshold without label channels, fraction of pixels
+ * with any foreground channel > mask_threshold with them), min, max of the channel sum}; deterministic. */
+int xvr_render_epilogue(const float* img, int B, int C, int N, float img_threshold, float mask_threshold,
+                        float* sum_img, float* stats, void* stream);
+
 /* out[r] = sum_n in[r,n], fixed summation tree */
 int xvr_reduce_rows(const float* in, int rows, int N, float* out, void* stream);
 

@@ -49,6 +49,7 @@ _SIGNATURES = {
     "xvr_hu_stats": ([P, ctypes.c_longlong, c_float, c_float, P, P, P], c_int),
     "xvr_hu_to_density": ([P, ctypes.c_longlong, c_float, c_float, c_float, P, P, P, P], c_int),
     "xvr_reduce_rows": ([P, c_int, c_int, P, P], c_int),
+    "xvr_render_epilogue": ([P, c_int, c_int, c_int, c_float, c_float, P, P, P], c_int),
     "xvr_euler_camera_fwd": ([P, P, c_int, ctypes.POINTER(c_int), c_int, ctypes.POINTER(c_float),
                               ctypes.POINTER(c_float), P, P, P], c_int),
     "xvr_euler_camera_bwd": ([P, P, c_int, ctypes.POINTER(c_int), c_int, ctypes.POINTER(c_float),

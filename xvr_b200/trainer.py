@@ -37,7 +37,7 @@ class PoseRegressor(torch.nn.Module):
 
     def __init__(self, model_name="resnet18", parameterization="quaternion_adjugate", convention="ZXY", pretrained=False,
                  height=256, unit_conversion_factor=1000.0, norm_layer="groupnorm", channels_last=False,
-                 backbone=None, **kwargs):
+                 backbone=None, autocast_bf16=False, **kwargs):
         super().__init__()
         if backbone is not None:
             # any feature extractor (B,1,H,W) -> (B,F); F probed like the reference does (network.py:40)
@@ -68,11 +68,19 @@ class PoseRegressor(torch.nn.Module):
         self.channels_last = bool(channels_last)
         if self.channels_last:
             self.backbone.to(memory_format=torch.channels_last)
+        # bf16 autocast around the BACKBONE only (dense convolutions: the one place tensor cores belong on this path);
+        # the two regression heads and the pose conversion stay in fp32.  Off by default: the reference trains in fp32.
+        self.autocast_bf16 = bool(autocast_bf16)
 
     def forward(self, x):
         if self.channels_last:
             x = x.contiguous(memory_format=torch.channels_last)
-        x = self.backbone(x)
+        if self.autocast_bf16 and x.is_cuda:
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                x = self.backbone(x)
+            x = x.float()
+        else:
+            x = self.backbone(x)
         rot = self.rot_regression(x)
         xyz = self.unit_conversion_factor * self.xyz_regression(x)
         return convert(rot, xyz, parameterization=self.parameterization, convention=self.convention)
@@ -162,6 +170,51 @@ def render_samples(drr, volume, seg, affinv, pose, img_threshold=0.10, mask_thre
     else:
         keep = (mask[:, 1:].sum(dim=1, keepdim=True) > 0).to(img).flatten(1).mean(1) > mask_threshold
     return img, mask, keep
+
+
+class _RenderEpilogue(torch.autograd.Function):
+    """(B,C,N) rendered channels -> (channel sum (B,1,N), stats (B,4) = {foreground fraction, keep, min, max}) in one
+    launch (csrc/train.cu); the backward hands the gradient of the sum back as an expanded view, which the renderer's
+    backward recognises (one upstream gradient per ray -> the saved Jacobian serves)."""
+
+    @staticmethod
+    def forward(ctx, img, img_threshold, mask_threshold):
+        from ._lib import call, cuda_f32, ptr, stream  # noqa: PLC0415
+
+        img = cuda_f32(img, "rendered batch")
+        B, C, N = img.shape
+        ctx.C = C
+        stats = torch.empty(B, 4, device=img.device, dtype=torch.float32)
+        total = img if C == 1 else torch.empty(B, 1, N, device=img.device, dtype=torch.float32)
+        if B > 0:
+            call("xvr_render_epilogue", ptr(img), B, C, N, float(img_threshold), float(mask_threshold),
+                 None if C == 1 else ptr(total), ptr(stats), stream())
+        ctx.mark_non_differentiable(stats)
+        return total.view(B, 1, N), stats
+
+    @staticmethod
+    def backward(ctx, gsum, _gstats):
+        return gsum.expand(-1, ctx.C, -1), None, None
+
+
+def render_samples_fused(drr, volume, seg, affinv, pose, img_threshold=0.10, mask_threshold=0.05):
+    """``render_samples`` through the fused kernels: without label channels the rays are generated inside the renderer
+    (no (B,N,3) tensors: 0.5 GB per batch at 256^2), and mask / channel sum / keep / per-sample min and max come out of
+    one epilogue launch.  Returns ``(img (B,1,H,W), mask (B,C,H,W) bool or None, keep (B,) bool, stats (B,4))``;
+    ``mask`` is only formed with label channels (the Dice term is a constant without them)."""
+    B = len(pose)
+    if seg is None and hasattr(drr.renderer, "render_drr"):
+        cam2world = drr.detector.reorient.compose(pose).matrix
+        cam2vox = affinv.matrix.to(cam2world) @ cam2world
+        raw = drr.renderer.render_drr(volume, cam2vox[:, :3].contiguous(), cam2world[:, :3].contiguous(), drr.detector)
+    else:
+        source, target = drr.detector(pose, None)
+        raylen = (target - source).norm(dim=-1).unsqueeze(1)
+        raw = drr.renderer(volume, affinv(source), affinv(target), raylen, mask=seg)
+    total, stats = _RenderEpilogue.apply(raw, img_threshold, mask_threshold)
+    H, W = drr.detector.height, drr.detector.width
+    mask = (raw.detach() > 0).view(B, -1, H, W) if seg is not None else None
+    return total.view(B, 1, H, W), mask, stats[:, 1] > 0, stats
 
 
 class TrainStep:
@@ -325,15 +378,22 @@ class TrainStep:
     #     (Adam(capturable=True) with a tensor lr, set from the same WarmupCosineSchedule formula);
     #   * the density goes to a static buffer and its texture upload is part of the captured work;
     #   * collectives (kept count, log sums, min/max, gradient all-reduce) are captured NCCL calls.
-    def _standardize_masked(self, x, keep):
+    def _standardize_masked(self, x, keep, stats=None):
         """XrayTransforms whose batch-global min/max run over the KEPT samples only (the reference standardises
-        img[keep]); with nothing kept anywhere the range falls back to [0, 1] and every weight is 0 anyway."""
-        sel = keep.view(-1, 1, 1, 1)
-        lo = torch.where(sel, x.detach(), torch.full_like(x, float("inf"))).min()
-        hi = torch.where(sel, x.detach(), torch.full_like(x, float("-inf"))).max()
+        img[keep]); with nothing kept anywhere the range falls back to [0, 1] and every weight is 0 anyway.
+        ``stats`` (B,4) from the render epilogue carries the per-sample min / max already: the batch-global range is
+        then a reduction over B numbers, and the ranks exchange it in ONE collective (max of [-lo, hi])."""
+        if stats is not None:
+            lo = torch.where(keep, stats[:, 2], torch.full_like(stats[:, 2], float("inf"))).min()
+            hi = torch.where(keep, stats[:, 3], torch.full_like(stats[:, 3], float("-inf"))).max()
+        else:
+            sel = keep.view(-1, 1, 1, 1)
+            lo = torch.where(sel, x.detach(), torch.full_like(x, float("inf"))).min()
+            hi = torch.where(sel, x.detach(), torch.full_like(x, float("-inf"))).max()
         if self.standardize_global:
-            dist.all_reduce(lo, op=dist.ReduceOp.MIN)
-            dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+            lohi = torch.stack([-lo, hi])
+            dist.all_reduce(lohi, op=dist.ReduceOp.MAX)
+            lo, hi = -lohi[0], lohi[1]
         lo = torch.where(torch.isfinite(lo), lo, torch.zeros_like(lo))
         hi = torch.where(torch.isfinite(hi), hi, torch.ones_like(hi))
         t = self.transforms
@@ -376,15 +436,17 @@ class TrainStep:
         if density_out is not None and hasattr(self.drr.renderer, "_texture"):
             self.drr.renderer._texture.invalidate()  # the buffer is rewritten through its raw pointer: upload again
         with torch.no_grad():
-            img, mask, keep = render_samples(self.drr, density, seg, affinv, pose)
+            img, mask, keep, stats = render_samples_fused(self.drr, density, seg, affinv, pose)
         w = keep.to(torch.float32)
         kept = w.sum().reshape(1)
         if self.world > 1:
             dist.all_reduce(kept, op=dist.ReduceOp.SUM)
-        x = self._standardize_masked(img, keep)
+        x = self._standardize_masked(img, keep, stats)
         pred_pose = self.model(x)
-        pred_img, pred_mask, _ = render_samples(self.drr, density, seg, affinv, pred_pose)
-        x_pred = self._standardize_masked(pred_img, keep)
+        pred_img, pred_mask, _, pred_stats = render_samples_fused(self.drr, density, seg, affinv, pred_pose)
+        x_pred = self._standardize_masked(pred_img, keep, pred_stats)
+        if mask is None:  # no label channels: the Dice term is the constant 1 (DiceLoss on one-channel masks)
+            mask = pred_mask = torch.ones(len(w), 1, 1, 1, device=w.device, dtype=torch.bool)
         loss, mncc, dgeo, rgeo, tgeo, dice, _ = self.lossfn(x, mask, pose, x_pred, pred_mask, pred_pose)
         denom = kept.clamp_min(1.0)
         ((loss * w).sum() / denom / self.n_grad_accum_itrs).backward()
