@@ -85,15 +85,18 @@ def summarise_launches(path):
 
 
 g = os.path.join(ROOT, "gpurun_out")
-if os.path.exists(os.path.join(g, "launches.csv")):
-    summarise_launches(os.path.join(g, "launches.csv"))
+if os.path.exists(os.path.join(g, f"{tag}_launches.csv")):
+    summarise_launches(os.path.join(g, f"{tag}_launches.csv"))
 tr = {}
-for rep, name, entry in (("prof_trilinear_fwd.ncu-rep", "trilinear_fwd", "xvr_trilinear_drr_fwd"),):
+# (report, summary name, C-ABI entry point whose launch it is, poses in the captured launch)
+for rep, name, entry, batch in ((f"{tag}_prof_trilinear_fwd.ncu-rep", "trilinear_fwd", "xvr_trilinear_drr_fwd", 116),
+                                (f"{tag}_prof_siddon_fwd.ncu-rep", "siddon_fwd", "xvr_siddon_drr_fwd", 32),
+                                (f"{tag}_prof_staged.ncu-rep", "trilinear_staged", "xvr_trilinear_drr_fwd_staged", 116)):
     if os.path.exists(os.path.join(g, rep)):
         t = summarise_full(os.path.join(g, rep), name)
-        tr[entry] = {"dram_bytes_per_launch": max(t.values()), "batch": 116,
-                     "source": f"profiles/{tag}_{name}_ncu_full.md"}
-for rep, name in (("prof_siddon_fwd.ncu-rep", "siddon_fwd"), ("prof_volgrad.ncu-rep", "volume_grad")):
+        tr[entry] = {"dram_bytes_per_launch": max(t.values()), "batch": batch,
+                     "source": f"profiles/{tag}_{name}_ncu_full.md (ncu --set full capture, not the timed run)"}
+for rep, name in ((f"{tag}_prof_volgrad.ncu-rep", "volume_grad_brick"), (f"{tag}_prof_siddon_volgrad.ncu-rep", "siddon_volume_grad")):
     if os.path.exists(os.path.join(g, rep)):
         summarise_full(os.path.join(g, rep), name)
 if os.path.exists(os.path.join(g, "kernels.log")):
@@ -109,6 +112,6 @@ if tr:
     old.update(tr)
     json.dump(old, open(path, "w"), indent=1)
 for f in ("bench_N1.json", "bench_ref.json"):
-    if os.path.exists(os.path.join(g, f)):
-        open(os.path.join(out, f"{tag}_{f}"), "w").write(open(os.path.join(g, f)).read())
+    if os.path.exists(os.path.join(g, f"{tag}_{f}")):
+        open(os.path.join(out, f"{tag}_{f}"), "w").write(open(os.path.join(g, f"{tag}_{f}")).read())
 print(os.listdir(out))
