@@ -136,9 +136,13 @@ def pose_batch(batch, seed):
     return torch.deg2rad(rot), xyz
 
 
-def build_scene(device, cfg):
+def build_scene(device, cfg, det=None, renderer="trilinear"):
+    """The DRR module of a configuration (`cfg` = an entry of CONFIGS, or a volume edge with `det` for the scripts)."""
     import xvr_b200
     from xvr_b200.data import read, synthetic_ct
+
+    if not isinstance(cfg, dict):
+        cfg = dict(vol=int(cfg), det=int(det), renderer=renderer)
 
     hu, _, affine = synthetic_ct(cfg["vol"], seed=0, device=device)
     sub = read(hu, affine=affine)

@@ -112,7 +112,7 @@ def section_siddon():
     idx = torch.zeros(Bs, N, 1, dtype=torch.int32, device=dev)
     seg = torch.zeros(Bs, N, 1, device=dev)
     _lib.call("xvr_siddon_trace", _lib.ptr(sdrr.density), *sdrr.density.shape, _lib.ptr(src), _lib.ptr(tgt), Bs, N, 0.5, 1e-8, 1,
-              _lib.ptr(idx), _lib.ptr(seg), _lib.ptr(cnt), _lib.stream())
+              _lib.ptr(idx), _lib.ptr(seg), _lib.ptr(cnt), _lib.opts_word(), _lib.stream())
     nseg = cnt.sum().item()
     print(json.dumps({"siddon_mean_segments_per_ray": nseg / (Bs * N)}))
     A_sid = nseg * 4 + Bs * N * 4

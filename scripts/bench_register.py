@@ -5,8 +5,8 @@ import torch
 import bench, xvr_b200
 from xvr_b200.registrar import Registrar
 
-# usage: bench_register.py [volume size] [--fused-similarity]   (the flag selects xvr_regsim)
-fused = "--fused-similarity" in sys.argv
+# usage: bench_register.py [volume size] [--unfused-similarity]   (default: xvr_regsim)
+fused = "--unfused-similarity" not in sys.argv
 args = [a for a in sys.argv[1:] if not a.startswith("--")]
 vol = int(args[0]) if args else 512
 drr = bench.build_scene(torch.device("cuda"), vol, 256)

@@ -4,7 +4,7 @@ import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import bench, xvr_b200
-from xvr_b200._lib import call, ptr, stream
+from xvr_b200._lib import call, options, opts_word, ptr, stream
 from xvr_b200.data import read, synthetic_ct
 
 dev = torch.device("cuda")
@@ -24,14 +24,13 @@ for seed in (0, 1):
         idx = torch.full((B, N, M), -2, dtype=torch.int32, device=dev)
         seg = torch.zeros(B, N, M, device=dev)
         cnt = torch.zeros(B, N, dtype=torch.int32, device=dev)
-        call("xvr_set_siddon_index_tol_scale", float(scale))
-        call("xvr_siddon_trace", ptr(drr.density), *drr.density.shape, ptr(src), ptr(tgt), B, N, 0.5, 1e-8, M, ptr(idx), ptr(seg),
-             ptr(cnt), stream())
-        call("xvr_set_siddon_index_tol_scale", 1.0)
+        with options(siddon_tol=scale):  # per-call option word (include/xvr_b200.h XVR_OPT_SIDDON_TOL)
+            call("xvr_siddon_trace", ptr(drr.density), *drr.density.shape, ptr(src), ptr(tgt), B, N, 0.5, 1e-8, M, ptr(idx),
+                 ptr(seg), ptr(cnt), opts_word(), stream())
         return idx, cnt
 
-    exact, cnt = trace(1e30)
-    for scale in (1.0, 0.5, 0.25, 0.125, 0.06, 0.03, 0.0):
+    exact, cnt = trace("exact")
+    for scale in ("production", 0.5, 0.25, 0.125):
         idx, _ = trace(scale)
         out[f"seed{seed}/scale{scale}"] = int((idx != exact).sum().item())
     out[f"seed{seed}/segments"] = int(cnt.sum().item())

@@ -436,7 +436,7 @@ def test_fused_registration_similarity_host_wiring(monkeypatch):
     assert Registrar(drr, fused_similarity=True).fused_similarity
     assert not Registrar(drr, fused_similarity=True, equalize=True).fused_similarity
     assert not Registrar(drr, fused_similarity=True, sigma=1.0).fused_similarity
-    assert not Registrar(drr).fused_similarity
+    assert Registrar(drr).fused_similarity and not Registrar(drr, fused_similarity=False).fused_similarity
 
 
 # ------------------------------------------------------------------------------------------------ round-2 additions

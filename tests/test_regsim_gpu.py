@@ -1,6 +1,7 @@
 """xvr_regsim -- value and gradient of the registration similarity in nine launches (csrc/ncc.cu) --
 against the composition it replaces, and the registration loop with it switched on.  Passed on the B200 at the end
-of round 1; the Registrar keeps it opt-in (``fused_similarity=True``) until it has been timed."""
+of round 1; timed in round 2 (faster once its prologue / epilogue became thread-block-cluster kernels) and now the
+Registrar's default."""
 
 import pytest
 import torch

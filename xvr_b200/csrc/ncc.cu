@@ -8,7 +8,11 @@
 // reads it from a shared-memory tile.  The backward pass is a gather: d ncc / d x_i over the windows containing
 // pixel i is  sum_w A_w (x1_i - mu1_w) - B_w (x2_i - mu2_w)  with four per-window coefficients saved by the
 // forward pass, i.e. a p x p gather from a shared-memory tile -- no atomics, deterministic.
+#include <cooperative_groups.h>
+
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace xvr {
 
@@ -292,8 +296,12 @@ sobel_bwd_kernel(const float* __restrict__ gout, int H, int W, float* __restrict
 // already transformed X-ray f (/root/reference/src/xvr/registrar/base.py:245-252, utils/preprocess.py:5-29), and
 // immediately differentiates it.  Composed from tensor ops that is ~60 launches around six real kernels; the three
 // kernels below supply the ends (standardise + Sobel in, score out, standardise-backward out) so that the whole
-// value-and-gradient evaluation is nine launches.  They run as ONE CTA each: a registration batch is a single
-// 256 x 256 image (64 elements per thread), and a single CTA needs no second launch for its reductions.
+// value-and-gradient evaluation is nine launches.  The two ends that touch every pixel run as ONE THREAD-BLOCK
+// CLUSTER of RS_CLUSTER CTAs each: a registration batch is a single 256 x 256 image, the batch-global min / max / tie
+// counts / gradient sums are exchanged through distributed shared memory behind cluster barriers (fixed order:
+// deterministic), so the reductions need no second launch and the pixels are spread over RS_CLUSTER SMs.
+// (Round 1 ran them as one CTA: three passes over 65 536 pixels on a single SM cost ~150 us each and made the fused
+// path slower than the ~50 small launches it replaces.)
 
 // Fixed-tree reductions over a 1024-thread CTA; every thread receives the result.
 template <typename T, typename Op>
@@ -309,42 +317,63 @@ __device__ __forceinline__ T cta1024_reduce(T v, Op op, T* red) {
   return v;
 }
 
+constexpr int RS_CLUSTER = 8;  // CTAs per cluster (portable maximum)
+
+// value of `mine` from every CTA of the cluster, combined in rank order (deterministic); `slot` is a __shared__ word
+template <typename T, typename Op>
+__device__ __forceinline__ T cluster_combine(cg::cluster_group& cluster, T* slot, T mine, Op op) {
+  if (threadIdx.x == 0) *slot = mine;
+  cluster.sync();
+  T v = *cluster.map_shared_rank(slot, 0);
+  for (unsigned r = 1; r < cluster.num_blocks(); ++r) v = op(v, *cluster.map_shared_rank(slot, r));
+  cluster.sync();  // nobody overwrites its slot (or exits) while a peer still reads it
+  return v;
+}
+
 // stats = {min, max, #elements equal to min, #elements equal to max, max - min + e}; ones (B) <- 1;
 // y (B,1,H,W) <- XrayTransforms(x); sob (B,2,H,W) <- Sobel(y) with zero padding in y-space (conv2d padding=1).
-__global__ void __launch_bounds__(1024)
+__global__ void __cluster_dims__(RS_CLUSTER, 1, 1) __launch_bounds__(1024)
 regsim_prep_kernel(const float* __restrict__ x, int B, int H, int W, float std_eps, float mean, float inv_std,
                    float* __restrict__ stats, float* __restrict__ ones, float* __restrict__ y,
                    float* __restrict__ sob) {
   __shared__ float redf[32];
   __shared__ int redi[32];
+  __shared__ float slot_f;
+  __shared__ int slot_i;
+  cg::cluster_group cluster = cg::this_cluster();
   const int tid = threadIdx.x;
+  const int gtid = (int)cluster.block_rank() * 1024 + tid, stride = (int)cluster.num_blocks() * 1024;
   const int HW = H * W, n = B * HW;
   float lo = INFINITY, hi = -INFINITY;
-  for (int i = tid; i < n; i += 1024) {
+  for (int i = gtid; i < n; i += stride) {
     const float v = __ldg(x + i);
     lo = fminf(lo, v);
     hi = fmaxf(hi, v);
   }
   lo = cta1024_reduce(lo, [](float a, float b) { return fminf(a, b); }, redf);
+  lo = cluster_combine(cluster, &slot_f, lo, [](float a, float b) { return fminf(a, b); });
   hi = cta1024_reduce(hi, [](float a, float b) { return fmaxf(a, b); }, redf);
+  hi = cluster_combine(cluster, &slot_f, hi, [](float a, float b) { return fmaxf(a, b); });
   int nlo = 0, nhi = 0;
-  for (int i = tid; i < n; i += 1024) {
+  for (int i = gtid; i < n; i += stride) {
     const float v = __ldg(x + i);
     nlo += v == lo;
     nhi += v == hi;
   }
   nlo = cta1024_reduce(nlo, [](int a, int b) { return a + b; }, redi);
+  nlo = cluster_combine(cluster, &slot_i, nlo, [](int a, int b) { return a + b; });
   nhi = cta1024_reduce(nhi, [](int a, int b) { return a + b; }, redi);
+  nhi = cluster_combine(cluster, &slot_i, nhi, [](int a, int b) { return a + b; });
   const float r = (hi - lo) + std_eps;
-  if (tid == 0) {
+  if (gtid == 0) {
     stats[0] = lo;
     stats[1] = hi;
     stats[2] = (float)nlo;
     stats[3] = (float)nhi;
     stats[4] = r;
   }
-  for (int b = tid; b < B; b += 1024) ones[b] = 1.f;
-  for (int i = tid; i < n; i += 1024) {
+  for (int b = gtid; b < B; b += stride) ones[b] = 1.f;
+  for (int i = gtid; i < n; i += stride) {
     const int b = i / HW, rem = i - b * HW;
     const int py = rem / W, px = rem - py * W;
     const float* im = x + (int64_t)b * HW;
@@ -381,17 +410,19 @@ regsim_score_kernel(const float* __restrict__ gstat, int B, float w_g, const flo
 // over ties, as torch's min()/max() backward distributes it):
 //   dS/dx_j = a g_j + [x_j = lo] (c S1 - a S0) / n_lo - [x_j = hi] c S1 / n_hi,
 //   a = inv_std / r, c = inv_std / r^2, S0 = sum g, S1 = sum g (x - lo).
-__global__ void __launch_bounds__(1024)
+__global__ void __cluster_dims__(RS_CLUSTER, 1, 1) __launch_bounds__(1024)
 regsim_bwd_finish_kernel(const float* __restrict__ x, const float* __restrict__ g_sob, const float* __restrict__ stats,
                          int B, int H, int W, float inv_std, float* __restrict__ g_y, float* __restrict__ grad) {
   __shared__ float redf[32];
-  const int tid = threadIdx.x;
+  __shared__ float slot_f;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int tid = (int)cluster.block_rank() * 1024 + threadIdx.x, stride = (int)cluster.num_blocks() * 1024;
   const int HW = H * W, n = B * HW;
   const float lo = stats[0], hi = stats[1], nlo = stats[2], nhi = stats[3], r = stats[4];
   const float kx[3][3] = {{1.f, 0.f, -1.f}, {2.f, 0.f, -2.f}, {1.f, 0.f, -1.f}};
   const float ky[3][3] = {{1.f, 2.f, 1.f}, {0.f, 0.f, 0.f}, {-1.f, -2.f, -1.f}};
   float s0 = 0.f, s1 = 0.f;
-  for (int i = tid; i < n; i += 1024) {
+  for (int i = tid; i < n; i += stride) {
     const int b = i / HW, rem = i - b * HW;
     const int py = rem / W, px = rem - py * W;
     const float* g0 = g_sob + (int64_t)b * 2 * HW;
@@ -410,12 +441,14 @@ regsim_bwd_finish_kernel(const float* __restrict__ x, const float* __restrict__ 
     s0 += g;
     s1 = fmaf(g, __ldg(x + i) - lo, s1);
   }
-  const float S0 = cta1024_reduce(s0, [](float a, float b) { return a + b; }, redf);
-  const float S1 = cta1024_reduce(s1, [](float a, float b) { return a + b; }, redf);
+  float S0 = cta1024_reduce(s0, [](float a, float b) { return a + b; }, redf);
+  S0 = cluster_combine(cluster, &slot_f, S0, [](float a, float b) { return a + b; });
+  float S1 = cta1024_reduce(s1, [](float a, float b) { return a + b; }, redf);
+  S1 = cluster_combine(cluster, &slot_f, S1, [](float a, float b) { return a + b; });
   const float a = inv_std / r;
   const float cS1 = inv_std * S1 / (r * r);
   const float t_lo = (cS1 - a * S0) / nlo, t_hi = -cS1 / nhi;
-  for (int i = tid; i < n; i += 1024) {  // every thread re-reads only what it wrote itself
+  for (int i = tid; i < n; i += stride) {  // every thread re-reads only what it wrote itself
     const float v = __ldg(x + i);
     float out = a * g_y[i];
     if (v == lo) out += t_lo;
@@ -571,7 +604,7 @@ extern "C" int xvr_regsim(const float* fixed, const float* fixed_sobel, const fl
   float* ws = workspace;
   const int HW = H * W;
   int rc;
-  regsim_prep_kernel<<<1, 1024, 0, st>>>(moving, B, H, W, std_eps, mean, inv_std, ws + L.stats, ws + L.ones, ws + L.y,
+  regsim_prep_kernel<<<RS_CLUSTER, 1024, 0, st>>>(moving, B, H, W, std_eps, mean, inv_std, ws + L.stats, ws + L.ones, ws + L.y,
                                          ws + L.sob);
   if ((rc = check_launch("xvr_regsim/prep"))) return rc;
 
@@ -607,6 +640,6 @@ extern "C" int xvr_regsim(const float* fixed, const float* fixed_sobel, const fl
                          ncc_smem(q, 4), st>>>(fixed_sobel, ws + L.sob, ws + L.coef_s, ws + L.ones,
                                                w_grad / (2.f * nHq * nWq * q * q), 2, H, W, q, ws + L.g_sob, 0);
   if ((rc = check_launch("xvr_regsim/gradient patch bwd"))) return rc;
-  regsim_bwd_finish_kernel<<<1, 1024, 0, st>>>(moving, ws + L.g_sob, ws + L.stats, B, H, W, inv_std, ws + L.g_y, grad);
+  regsim_bwd_finish_kernel<<<RS_CLUSTER, 1024, 0, st>>>(moving, ws + L.g_sob, ws + L.stats, B, H, W, inv_std, ws + L.g_y, grad);
   return check_launch("xvr_regsim/finish");
 }
