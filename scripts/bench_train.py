@@ -29,6 +29,9 @@ ap.add_argument("--channels-last", action="store_true")
 ap.add_argument("--bf16", action="store_true", help="bf16 autocast around the CNN (tensor-core convolutions)")
 ap.add_argument("--init", default="near-truth", choices=["near-truth", "random"])
 ap.add_argument("--profile", action="store_true")
+ap.add_argument("--shard", default="batch", choices=["batch", "accumulation"],
+                help="batch: every iteration split over all ranks; accumulation: the 4 iterations of an optimiser step "
+                     "dealt out to groups of ranks (TrainStep docstring)")
 args = ap.parse_args()
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
@@ -65,14 +68,25 @@ if args.init == "near-truth":
         model.xyz_regression.weight.mul_(0.05)
 step = TrainStep(drr, model, volumes, bench.POSE_RANGES, XrayTransforms(args.height), bench.SDD, batch_size=args.batch,
                  n_grad_accum_itrs=4, n_warmup_itrs=8, use_cuda_graph=args.graph,
-                 log_every=args.log_every if args.graph else 1)
+                 log_every=args.log_every if args.graph else 1, shard=args.shard)
 i0 = 0
 for i0 in range(args.warmup):
     log = step.step(i0)
 i0 = args.warmup
-while args.graph and (len(step._graphs) < args.n_vols or step._opt_graph is None):  # capture every subject's graph
-    log = step.step(i0)
-    i0 += 1
+def everything_captured():
+    """Every rank has captured every subject's graph and the optimiser graph (ranks own different iterations when the
+    accumulation window is sharded: agree on it collectively, at a window boundary)."""
+    ok = torch.tensor([float(len(step._graphs) >= args.n_vols and step._opt_graph is not None)], device=dev)
+    if world > 1:
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    return bool(ok.item())
+
+
+i0 += (-i0) % 4
+while args.graph and not everything_captured():
+    for _ in range(4):
+        log = step.step(i0)
+        i0 += 1
 torch.cuda.synchronize()
 if world > 1:
     dist.barrier()
@@ -103,7 +117,7 @@ elif args.profile:
 if rank == 0:
     ms = 1e3 * dt_dev.item() / args.steps
     print(json.dumps({"workload": f"xvr train step: {args.n_vols} x {args.vol}^3 volumes, global batch {args.batch} sharded over {world} GPU(s), "
-                      f"{args.height}^2 DRRs, resnet18+GroupNorm, 2 renders/step, labels={args.labels}, cuda_graph={args.graph}, "
+                      f"{args.height}^2 DRRs, resnet18+GroupNorm, 2 renders/step, labels={args.labels}, cuda_graph={args.graph}, shard={args.shard}, "
                       f"channels_last={args.channels_last}, bf16={args.bf16}, init={args.init}",
                       "n_gpus": world, "ms_per_step": ms, "ms_per_step_wall": 1e3 * dt / args.steps, "steps_per_s": 1e3 / ms,
                       "drrs_per_s": 2 * args.batch * 1e3 / ms, "last_log": log}))

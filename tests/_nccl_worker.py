@@ -53,24 +53,28 @@ for _ in range(4):
     draws.append((0, float(torch.empty(1).uniform_(1.0, 10.0, generator=g)), r, x))
 
 
-def run(sharded):
+def run(mode):
+    """mode: "batch" (every iteration split over the ranks), "accumulation" (the two iterations of a window on one rank
+    each, full batch), "single" (everything on this rank, no collectives)."""
     torch.manual_seed(0)
     model = PoseRegressor("resnet18", "quaternion_adjugate", "ZXY", height=h, norm_layer="groupnorm").to(dev)
     with torch.no_grad():
         model.xyz_regression.bias.copy_(torch.tensor([0.0, 0.8 + center[1].item() / 1000.0, 0.0]))
         model.rot_regression.bias.copy_(torch.tensor([1.0, 0, 0, 0, 0, 0, 0, 0, 0, 0]))
-    step = TrainStep(drr, model, volumes, ranges, XrayTransforms(h), SDD, batch_size=B, n_grad_accum_itrs=2, n_warmup_itrs=2)
-    if not sharded:  # the whole batch on this rank, no collectives -- same masked arithmetic
+    step = TrainStep(drr, model, volumes, ranges, XrayTransforms(h), SDD, batch_size=B, n_grad_accum_itrs=2, n_warmup_itrs=2,
+                     shard="accumulation" if mode == "accumulation" else "batch")
+    if mode == "single":  # the whole batch on this rank, no collectives -- same masked arithmetic
         step.world, step.rank, step.local_batch, step.standardize_global = 1, 0, B, False
-    a, b = shard_bounds(B, step.rank, step.world)
+        step.n_groups, step.sub_world, step.sub_rank, step.group_index = 1, 1, 0, 0
+    a, b = shard_bounds(B, step.sub_rank, step.sub_world)
     it = iter(draws)
     step._draw = lambda itr: (lambda d: (d[0], d[1], d[2][a:b], d[3][a:b]))(next(it))
     logs = [step._step_masked_eager(i) for i in range(4)]
     return logs, torch.cat([p.detach().reshape(-1) for p in model.parameters()])
 
 
-logs_s, w_s = run(True)
-logs_u, w_u = run(False)
+logs_s, w_s = run("batch")
+logs_u, w_u = run("single")
 for i, (ls, lu) in enumerate(zip(logs_s, logs_u)):
     # iterations 0 and 1 run on the initial weights (the first optimiser step follows iteration 1): only the order of
     # the fp32 sums differs.  Later iterations see weights that went through Adam, which turns rounding noise in
@@ -83,6 +87,19 @@ assert ((w_s - w_u).norm() / w_u.norm()).item() < 1e-4, "sharded and unsharded t
 ws = [torch.empty_like(w_s) for _ in range(world)]
 dist.all_gather(ws, w_s)
 assert all(torch.equal(w, ws[0]) for w in ws), "ranks hold different weights"
+
+# ---- 3. the accumulation window dealt out to the ranks (one full-batch iteration each, one gradient all-reduce per
+# optimiser step) against the single-rank run: same weights
+logs_a, w_a = run("accumulation")
+assert ((w_a - w_u).norm() / w_u.norm()).item() < 1e-4, "accumulation sharding diverged from the single-rank run"
+wa = [torch.empty_like(w_a) for _ in range(world)]
+dist.all_gather(wa, w_a)
+assert all(torch.equal(w, wa[0]) for w in wa), "ranks hold different weights (accumulation sharding)"
+own = [i for i in range(4) if (i % 2) % world == rank]
+for i in own:  # the iterations this rank ran itself carry the single-rank run's log values
+    for k in ("loss", "mncc", "dgeo", "kept"):
+        tol = 2e-5 if i < 2 else 3e-3
+        assert abs(logs_a[i][k] - logs_u[i][k]) <= tol * max(1.0, abs(logs_u[i][k])), (i, k, logs_a[i][k], logs_u[i][k])
 dist.barrier()
 if rank == 0:
     print("NCCL_WORKER_OK")

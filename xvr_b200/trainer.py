@@ -224,17 +224,46 @@ class TrainStep:
     RigidTransform) -- what ``Trainer.load`` (trainer.py:248-277) produces per subject.  Every rank must pass the
     same list; subject choice and contrast are drawn from a generator seeded identically on all ranks, the pose
     batch from a per-rank generator.
+
+    ``shard`` chooses how several ranks divide the work.  ``"batch"``: every iteration's batch is split over all
+    ranks (the renderer scales with it, the CNN at a per-rank batch of ~15 does not).  ``"accumulation"``: the
+    ``n_grad_accum_itrs`` iterations between two optimiser steps are independent given the weights, so they are
+    dealt out to groups of ranks -- with W <= A ranks every rank runs whole iterations at the full batch, with
+    W = g * A each iteration is split over a sub-group of g ranks -- and the gradients meet in ONE all-reduce per
+    optimiser step.  Same arithmetic as the reference's gradient accumulation (trainer.py:219-231), a CNN batch g
+    times larger than batch sharding gives it.
     """
 
     def __init__(self, drr, model, volumes, pose_distribution, transforms, sdd, batch_size=116, lr=2e-4,
                  n_total_itrs=1_000_000, n_warmup_itrs=1_000, n_grad_accum_itrs=4, weight_ncc=1.0, weight_geo=1e-2,
                  weight_dice=1.0, weight_mvc=0.0, seed=0, standardize_global=True, disable_scheduler=False,
-                 use_cuda_graph=False, log_every=1):
+                 use_cuda_graph=False, log_every=1, shard="batch"):
         self.rank, self.world = _world()
         self.drr, self.model, self.volumes, self.transforms = drr, model, volumes, transforms
         self.pose_distribution = dict(pose_distribution)
         self.batch_size = batch_size
-        lo, hi = shard_bounds(batch_size, self.rank, self.world)
+        self.seed = seed
+        # ---- who works on what: n_groups groups of sub_world ranks; group g owns the iterations with
+        # (itr mod n_grad_accum_itrs) mod n_groups == g and splits their batch over its sub_world ranks
+        if shard not in ("batch", "accumulation"):
+            raise ValueError("shard must be 'batch' or 'accumulation'")
+        self.n_groups, self.sub_world, self.sub_group = 1, self.world, None
+        if shard == "accumulation" and self.world > 1:
+            A = n_grad_accum_itrs
+            if self.world <= A and A % self.world == 0:
+                self.n_groups, self.sub_world = self.world, 1
+            elif self.world % A == 0:
+                self.n_groups, self.sub_world = A, self.world // A
+            else:
+                raise ValueError(f"shard='accumulation' needs world ({self.world}) to divide or be a multiple of "
+                                 f"n_grad_accum_itrs ({A})")
+            if self.sub_world > 1:  # every rank creates every group, in the same order
+                for g in range(self.n_groups):
+                    grp = dist.new_group(list(range(g * self.sub_world, (g + 1) * self.sub_world)))
+                    if g == self.rank // self.sub_world:
+                        self.sub_group = grp
+        self.group_index, self.sub_rank = self.rank // self.sub_world, self.rank % self.sub_world
+        lo, hi = shard_bounds(batch_size, self.sub_rank, self.sub_world)
         self.local_batch = hi - lo
         self.lossfn = PoseRegressionLoss(sdd, weight_ncc, weight_geo, weight_dice, weight_mvc)
         self.optimizer = torch.optim.Adam(model.parameters(), lr=lr)
@@ -246,7 +275,7 @@ class TrainStep:
         self.n_total_itrs, self.n_grad_accum_itrs = n_total_itrs, n_grad_accum_itrs
         self.shared_rng = torch.Generator().manual_seed(seed)           # same stream on every rank
         self.pose_rng = torch.Generator().manual_seed(seed * 9973 + 1 + self.rank)
-        self.standardize_global = standardize_global and self.world > 1
+        self.standardize_global = standardize_global and self.sub_world > 1
         self.device = next(model.parameters()).device
         self.use_cuda_graph = bool(use_cuda_graph)
         self.log_every = max(1, int(log_every))
@@ -278,8 +307,15 @@ class TrainStep:
         rank's own; tests replay recorded draws through this hook."""
         subject = int(torch.randint(len(self.volumes), (1,), generator=self.shared_rng))
         contrast = float(torch.empty(1).uniform_(1.0, 10.0, generator=self.shared_rng))
-        rot, xyz = random_pose_params(**self.pose_distribution, batch_size=self.local_batch, generator=self.pose_rng)
+        rng = self.pose_rng
+        if self.n_groups > 1:  # iterations run on different groups: the pose stream is a function of the iteration
+            rng = torch.Generator().manual_seed((self.seed * 9973 + 1 + self.sub_rank) * 1_000_003 + itr)
+        rot, xyz = random_pose_params(**self.pose_distribution, batch_size=self.local_batch, generator=rng)
         return subject, contrast, rot, xyz
+
+    def owns(self, itr):
+        """Does this rank's group work on iteration ``itr``?  (Always, unless the accumulation window is sharded.)"""
+        return (itr % self.n_grad_accum_itrs) % self.n_groups == self.group_index
 
     def step(self, itr):
         if self.use_cuda_graph:
@@ -392,7 +428,7 @@ class TrainStep:
             hi = torch.where(sel, x.detach(), torch.full_like(x, float("-inf"))).max()
         if self.standardize_global:
             lohi = torch.stack([-lo, hi])
-            dist.all_reduce(lohi, op=dist.ReduceOp.MAX)
+            dist.all_reduce(lohi, op=dist.ReduceOp.MAX, group=self.sub_group)
             lo, hi = -lohi[0], lohi[1]
         lo = torch.where(torch.isfinite(lo), lo, torch.zeros_like(lo))
         hi = torch.where(torch.isfinite(hi), hi, torch.ones_like(hi))
@@ -409,15 +445,20 @@ class TrainStep:
         that every rank issues the same collectives whatever it kept -- the same arithmetic as graph mode, without
         the capture."""
         dev = self.device
-        subject, contrast, rot, xyz = self._draw(itr)
-        log_dev = self._masked_iteration(subject, rot.to(dev), xyz.to(dev), contrast, None)
+        subject, contrast, rot, xyz = self._draw(itr)  # every rank draws every iteration: the shared stream stays in step
+        log_dev = None
+        if self.owns(itr):
+            log_dev = self._masked_iteration(subject, rot.to(dev), xyz.to(dev), contrast, None)
+            self._last_eager_log = log_dev
         if (itr + 1) % self.n_grad_accum_itrs == 0 or (itr + 1) == self.n_total_itrs:
             self._allreduce_grads()
             adaptive_clip_grad_(self.model.parameters())
             self.optimizer.step()
             self.scheduler.step()
             self.optimizer.zero_grad()
-        log = dict(zip(("loss", "mncc", "dgeo", "rgeo", "tgeo", "dice", "kept"), log_dev.tolist()))
+        log_dev = log_dev if log_dev is not None else getattr(self, "_last_eager_log", None)
+        vals = log_dev.tolist() if log_dev is not None else [float("nan")] * 7
+        log = dict(zip(("loss", "mncc", "dgeo", "rgeo", "tgeo", "dice", "kept"), vals))
         log["lr"] = self.scheduler.get_last_lr()[0]
         return log
 
@@ -439,8 +480,8 @@ class TrainStep:
             img, mask, keep, stats = render_samples_fused(self.drr, density, seg, affinv, pose)
         w = keep.to(torch.float32)
         kept = w.sum().reshape(1)
-        if self.world > 1:
-            dist.all_reduce(kept, op=dist.ReduceOp.SUM)
+        if self.sub_world > 1:
+            dist.all_reduce(kept, op=dist.ReduceOp.SUM, group=self.sub_group)
         x = self._standardize_masked(img, keep, stats)
         pred_pose = self.model(x)
         pred_img, pred_mask, _, pred_stats = render_samples_fused(self.drr, density, seg, affinv, pred_pose)
@@ -452,8 +493,8 @@ class TrainStep:
         ((loss * w).sum() / denom / self.n_grad_accum_itrs).backward()
         with torch.no_grad():
             sums = torch.stack([(v.detach() * w).sum() for v in (loss, mncc, dgeo, rgeo, tgeo, dice)])
-            if self.world > 1:
-                dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+            if self.sub_world > 1:
+                dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=self.sub_group)
             means = sums / denom
             means[0] /= self.n_grad_accum_itrs  # the reference logs the loss after dividing it for accumulation
             return torch.cat([means, kept / self.batch_size])
@@ -522,6 +563,8 @@ class TrainStep:
 
     def _step_graphed(self, itr):
         subject, contrast, rot, xyz = self._draw(itr)
+        if not self.owns(itr):  # another group's iteration of the accumulation window
+            return self._finish_graphed(itr)
         slot = itr % len(self._stage)
         rot_h, xyz_h, ev = self._stage[slot]
         if self._stage_used[slot]:
@@ -541,7 +584,9 @@ class TrainStep:
             for p, g in zip(self.model.parameters(), saved):
                 p.grad.copy_(g)
         self._graphs[subject].replay()
+        return self._finish_graphed(itr)
 
+    def _finish_graphed(self, itr):
         if (itr + 1) % self.n_grad_accum_itrs == 0 or (itr + 1) == self.n_total_itrs:
             if self._opt_graph is None:
                 self._opt_graph = self._capture_optimizer()
