@@ -284,6 +284,52 @@ def run_config(name, steps, warmup, rank, world, device, with_clocks=True):
         step(rot_d, xyz_d)
     barrier()
 
+    # ---- empty-space trimming (trilinear): the kernel skips samples outside the box of the volume's non-zero voxels
+    # (exact zeros, bit-identical output).  Measure what share of the samples it marches, and time the step once more
+    # with the trimming switched off so that both numbers are on the line.
+    trimming = None
+    if name == "trilinear":
+        import ctypes
+
+        from xvr_b200._lib import call, options, opts_word, ptr, stream
+        pose = xvr_b200.convert(rot_d, xyz_d, parameterization="euler_angles", convention="ZXY")
+        cam2world = drr.detector.reorient.compose(pose).matrix
+        cam2vox = (drr._affine_inverse @ cam2world)[:, :3].contiguous()
+        cam2world = cam2world[:, :3].contiguous()
+        origin, row_step, col_step = drr.detector.pixel_basis()
+        det9 = (ctypes.c_float * 9)(*origin, *row_step, *col_step)
+        handle = drr.renderer._texture.get(drr.density)
+        counts = []
+        for trim in (True, False):
+            counter = torch.zeros(1, dtype=torch.int64, device=device)
+            with options(trim=trim):
+                call("xvr_trilinear_drr_count", handle, *drr.density.shape, ptr(cam2vox), ptr(cam2world), det9, B, H, W,
+                     N_POINTS, float(drr.renderer.eps), ptr(counter), opts_word(), stream())
+            counts.append(int(counter.item()))
+        bbox = (ctypes.c_int * 6)()
+        call("xvr_volume_bbox", handle, bbox, stream())
+        k = max(3, min(steps, 10))
+        with options(trim=False):
+            for _ in range(2):
+                step(rot_d, xyz_d)
+            barrier()
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record()
+            for _ in range(k):
+                step(rot_d, xyz_d)
+            t1.record()
+            barrier()
+        t_off = torch.tensor([t0.elapsed_time(t1)], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t_off, op=dist.ReduceOp.MAX)
+        trimming = {"what": "samples whose 8 corners lie outside the box of the volume's non-zero voxels are skipped "
+                            "(exact zeros for every sum: images and Jacobians bit-identical to the full march, "
+                            "tests/test_trilinear_gpu.py::test_empty_space_trimming_is_bit_identical)",
+                    "nonzero_box": list(bbox), "samples_in_volume": counts[1], "samples_marched": counts[0],
+                    "marched_fraction": counts[0] / max(1, counts[1]),
+                    "value_without_trimming": world * B * k / (t_off.item() * 1e-3),
+                    "ms_per_step_without_trimming": t_off.item() / k}
+
     # ---- device-resident timing ("value")
     sampler = ClockSampler(device.index)
     if rank == 0 and with_clocks:
@@ -357,8 +403,12 @@ def run_config(name, steps, warmup, rank, world, device, with_clocks=True):
     if name == "trilinear":
         entry = next((k for k in ("xvr_trilinear_drr_fwd", "xvr_trilinear_drr_fwd_staged") if k in kernel_ms),
                      "xvr_trilinear_rays_fwd")
-        alg = B * H * W * (N_POINTS * 32 + 4)  # SURVEY 8(d) gather model: 8 corners x 4 B per sample + the pixel
-        alg_note = "B*H*W*(n_points*32+4): 8 corner voxels x 4 B per sample + the output pixel (gather model, no reuse)"
+        # SURVEY 8(d) gather model: 8 corners x 4 B per sample + the pixel -- over the samples the kernel MARCHES (the
+        # trimmed ones are never fetched; counting them would credit the kernel with bandwidth it does not use)
+        marched = trimming["samples_marched"] if trimming else B * H * W * N_POINTS
+        alg = marched * 32 + B * H * W * 4
+        alg_note = (f"samples_marched*32 + B*H*W*4: 8 corner voxels x 4 B per MARCHED sample ({marched} of "
+                    f"{B * H * W * N_POINTS}: empty-space trimming) + the output pixels (gather model, no reuse)")
         kernel = ("trilinear forward (+ per-ray pose Jacobian in the same march; the backward is a 28 B/ray epilogue)")
         two_pass = 2.0
     else:
@@ -398,6 +448,7 @@ def run_config(name, steps, warmup, rank, world, device, with_clocks=True):
                           "achieved": two_pass * alg * steps / (ms * 1e-3) / 1e9,
                           "frac": two_pass * alg * steps / (ms * 1e-3) / 1e9 / peak},
         "kernel_share_of_step": {k: sum(v) / ms for k, v in kernel_ms.items()},
+        **({"empty_space_trimming": trimming} if trimming else {}),
     }
 
 

@@ -27,6 +27,8 @@ extern "C" {
                                            * (small batches, B = 1 registration, split rays so that the SMs stay full) */
 #define XVR_OPT_SIDDON_WALK 0x10          /* Siddon: voxel indices from the integer walk (opt-in: same indices, measured slower) */
 #define XVR_OPT_VOLGRAD_GATHER 0x20       /* dL/dvolume: voxel-centric gather (cross-check) instead of the brick-local scatter */
+#define XVR_OPT_NO_TRIM 0x40              /* trilinear forward: march all n_points samples, also those outside the box of
+                                           * the volume's non-zero voxels (the default skips them: exact zeros) */
 #define XVR_OPT_SIDDON_TOL(code) ((code) << 8) /* test hook: tolerance of the fast voxel-index certificate; 0 production,
                                            * 1 always the reference's exact arithmetic, 2/3/4 = x 1/2, 1/4, 1/8 (margin probes) */
 
@@ -41,6 +43,17 @@ long long xvr_launch_count(void);
 int xvr_volume_create(int D0, int D1, int D2, void** handle_out);
 int xvr_volume_upload(void* handle, const float* volume, void* stream);
 int xvr_volume_destroy(void* handle);
+/* Every upload also records the box of the volume's NON-ZERO voxels (transform_hu_to_density maps air to exactly 0, and CT
+ * volumes carry wide margins of it): the trilinear forward kernels skip the samples whose 8 corners all lie outside it
+ * -- exact zeros for every running sum, so images and Jacobians are bit-identical to the full march
+ * (XVR_OPT_NO_TRIM switches it off).  bbox6: HOST int[6] = lo0 lo1 lo2 hi0 hi1 hi2 (lo = D, hi = -1 for an all-zero
+ * volume); synchronises `stream`. */
+int xvr_volume_bbox(void* handle, int* bbox6, void* stream);
+/* samples xvr_trilinear_drr_fwd marches for a batch (counter: zeroed DEVICE unsigned long long) -- bench.py's executed
+ * share under the trimming */
+int xvr_trilinear_drr_count(const void* voltex, int D0, int D1, int D2, const float* cam2vox, const float* cam2world,
+                            const float* det9, int B, int det_h, int det_w, int n_points, float eps,
+                            unsigned long long* counter, int opts, void* stream);
 
 /* ---- Trilinear renderer = diffdrr.renderers.Trilinear.forward
  * call site /root/reference/src/xvr/model/trainer.py:288  drr.renderer(vol, source, target, raylen, mask=seg)

@@ -360,3 +360,49 @@ def test_channel_collapsed_gradient_uses_the_saved_jacobian(cuda, renderer):
     # the unlabelled render takes the fused path (rays generated in registers, not read from (B,N,3) tensors): same
     # mathematics, different rounding of the ray end points -> the noisy-phantom gradient bar
     assert rel_l2(grads[0], grads[2]) < 2e-3
+
+
+# ------------------------------------------------------------------------------------------ empty-space trimming
+@pytest.mark.parametrize("scene", ["phantom", "blob", "dense", "zeros", "labels", "edge"])
+def test_empty_space_trimming_is_bit_identical(cuda, scene):
+    """The forward kernels skip samples outside the box of the volume's non-zero voxels (exact zeros for every sum):
+    images, label channels and pose gradients equal the full march bit for bit -- air margins, a small blob in a sea of
+    zeros, a volume without a single zero, an all-zero volume, label channels, rays missing / grazing / starting inside."""
+    import ctypes
+
+    from tests.test_zz_full_size_gpu import EDGE_ROT, EDGE_XYZ
+    from xvr_b200._lib import call, options
+
+    drr = make_drr(64, 40, with_labels=scene == "labels")
+    rot, xyz = pose_params(3, seed=17)
+    if scene == "blob":
+        vol = torch.zeros_like(drr.density)
+        vol[20:27, 40:44, 9:30] = torch.rand(7, 4, 21, device=cuda) + 0.1
+        drr.density = vol
+    elif scene == "dense":
+        drr.density = torch.rand_like(drr.density) + 0.5
+    elif scene == "zeros":
+        drr.density = torch.zeros_like(drr.density)
+    elif scene == "edge":
+        rot, xyz = torch.tensor(EDGE_ROT, device=cuda), torch.tensor(EDGE_XYZ, device=cuda)
+    outs = []
+    for trim in (True, False):
+        with options(trim=trim, ksplit=0):
+            r, x = rot.clone().requires_grad_(), xyz.clone().requires_grad_()
+            img = drr(xvr_b200.convert(r, x, parameterization="euler_angles", convention="ZXY"),
+                      mask_to_channels=scene == "labels")
+            w = torch.rand(img.shape, generator=torch.Generator().manual_seed(1)).to(cuda)
+            (img * w).sum().backward()
+            outs.append((img.detach().clone(), r.grad.clone(), x.grad.clone()))
+    for u, v in zip(*outs):
+        assert torch.equal(u, v)
+    # the handle reports the box it trims to
+    bbox = (ctypes.c_int * 6)()
+    call("xvr_volume_bbox", drr.renderer._texture.handle, bbox, None)
+    nz = (drr.density != 0).nonzero()
+    if scene == "zeros":
+        assert list(bbox) == [64, 64, 64, -1, -1, -1]
+    else:
+        assert list(bbox) == nz.min(0).values.tolist() + nz.max(0).values.tolist()
+    if scene == "blob":
+        assert outs[0][0].abs().sum() > 0

@@ -21,6 +21,9 @@ _SIGNATURES = {
     "xvr_volume_create": ([c_int, c_int, c_int, ctypes.POINTER(c_void_p)], c_int),
     "xvr_volume_upload": ([P, P, P], c_int),
     "xvr_volume_destroy": ([P], c_int),
+    "xvr_volume_bbox": ([P, ctypes.POINTER(c_int), P], c_int),
+    "xvr_trilinear_drr_count": ([P, c_int, c_int, c_int, P, P, ctypes.POINTER(c_float), c_int, c_int, c_int, c_int, c_float,
+                                 P, c_int, P], c_int),
     "xvr_trilinear_rays_fwd": (
         [P, P, c_int, c_int, c_int, P, c_int, P, P, P, c_int, c_int, c_int, c_int, c_float, c_int, c_int, c_int,
          c_int, P, P, c_int, P], c_int),
@@ -79,7 +82,7 @@ _SIGNATURES = {
 # ---- per-call kernel options (include/xvr_b200.h XVR_OPT_*).  The library itself keeps no mutable state: the
 # variant travels with every call.  This host-side holder only supplies the word; tests and tuning scripts change it
 # with `with options(siddon_walk=True): ...`.
-_OPTION_DEFAULTS = {"ksplit": None, "siddon_walk": False, "volgrad": "brick", "siddon_tol": "production"}
+_OPTION_DEFAULTS = {"ksplit": None, "siddon_walk": False, "volgrad": "brick", "siddon_tol": "production", "trim": True}
 _options = dict(_OPTION_DEFAULTS)
 _TOL_CODES = {"production": 0, "exact": 1, 0.5: 2, 0.25: 3, 0.125: 4}
 
@@ -96,6 +99,8 @@ def opts_word():
         w |= 0x20
     elif _options["volgrad"] != "brick":
         raise ValueError("volgrad must be 'brick' or 'gather'")
+    if not _options["trim"]:
+        w |= 0x40
     w |= _TOL_CODES[_options["siddon_tol"]] << 8
     return w
 

@@ -1,5 +1,6 @@
 // C-ABI plumbing shared by every entry point: error reporting and library identification.
 #include <stdio.h>
+#include <limits.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -37,6 +38,59 @@ extern "C" long long xvr_launch_count(void) { return xvr::g_launches; }
 // A second, block-linear copy of the CT volume (cudaArray, layered 2D: layer = axis 0 + 1, with one zero layer at
 // each end) behind a point-sampled texture object.  The trilinear kernels fetch the 2x2 (axis 1, axis 2) corner footprint of each of the two
 // layers with one TLD4 each instead of 8 scalar loads.
+namespace xvr {
+// Box of the non-zero voxels, for the marchers' empty-space trimming: CT volumes carry wide margins of air, which
+// transform_hu_to_density maps to exactly 0 -- samples whose 8 corners all lie outside this box contribute exact zeros
+// to every sum and need not be fetched.  One CTA per (axis-0 index, 8 axis-1 rows); integer atomics: deterministic.
+__global__ void volume_bbox_init_kernel(int* bbox, int D0, int D1, int D2) {
+  if (threadIdx.x < 3) bbox[threadIdx.x] = threadIdx.x == 0 ? D0 : (threadIdx.x == 1 ? D1 : D2);
+  else if (threadIdx.x < 6) bbox[threadIdx.x] = -1;
+}
+__global__ void __launch_bounds__(256) volume_bbox_kernel(const float* __restrict__ vol, int D1, int D2, int* bbox) {
+  __shared__ int s_any, s_ylo, s_yhi, s_zlo, s_zhi;
+  if (threadIdx.x == 0) { s_any = 0; s_ylo = INT_MAX; s_yhi = -1; s_zlo = INT_MAX; s_zhi = -1; }
+  __syncthreads();
+  const int x = blockIdx.y, y = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (y < D1) {
+    const float* row = vol + ((int64_t)x * D1 + y) * D2;
+    int zlo = INT_MAX, zhi = -1;
+    for (int z = lane; z < D2; z += 32)
+      if (row[z] != 0.f) { zlo = min(zlo, z); zhi = max(zhi, z); }
+    zlo = __reduce_min_sync(0xffffffffu, zlo);
+    zhi = __reduce_max_sync(0xffffffffu, zhi);
+    if (lane == 0 && zhi >= 0) {
+      atomicOr(&s_any, 1);
+      atomicMin(&s_ylo, y); atomicMax(&s_yhi, y);
+      atomicMin(&s_zlo, zlo); atomicMax(&s_zhi, zhi);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && s_any) {
+    atomicMin(bbox + 0, x); atomicMax(bbox + 3, x);
+    atomicMin(bbox + 1, s_ylo); atomicMax(bbox + 4, s_yhi);
+    atomicMin(bbox + 2, s_zlo); atomicMax(bbox + 5, s_zhi);
+  }
+}
+// Occupancy of OCC_BRICK^3 bricks: 1 if the brick GROWN BY TWO VOXELS on every side holds a non-zero voxel -- a sample
+// whose cell floor(x) lies in an unoccupied brick reads 8 zero corners (floor(x) + 1 is inside the brick grown by one),
+// with one more voxel for rays that graze a brick face within rounding (trim_to_occupied_bricks, csrc/trilinear.cu).
+__global__ void __launch_bounds__(256) volume_occupancy_kernel(const float* __restrict__ vol, int D0, int D1, int D2,
+                                                               int nb1, int nb2, uint8_t* __restrict__ occ) {
+  const int b = blockIdx.x;
+  const int bx = b / (nb1 * nb2), by = (b / nb2) % nb1, bz = b % nb2;
+  constexpr int G = OCC_BRICK + 4;
+  const int x0 = bx * OCC_BRICK - 2, y0 = by * OCC_BRICK - 2, z0 = bz * OCC_BRICK - 2;
+  int any = 0;
+  for (int i = threadIdx.x; i < G * G * G && !any; i += 256) {
+    const int x = x0 + i / (G * G), y = y0 + (i / G) % G, z = z0 + i % G;
+    if ((unsigned)x < (unsigned)D0 && (unsigned)y < (unsigned)D1 && (unsigned)z < (unsigned)D2)
+      any = vol[((int64_t)x * D1 + y) * D2 + z] != 0.f;
+  }
+  any = __syncthreads_or(any);
+  if (threadIdx.x == 0) occ[b] = any ? 1 : 0;
+}
+}  // namespace xvr
+
 extern "C" int xvr_volume_create(int D0, int D1, int D2, void** out) {
   if (!out || D0 < 1 || D1 < 1 || D2 < 1 || D0 > 2046 || D1 > 32768 || D2 > 32768) {
     xvr::set_last_error("xvr_volume_create: invalid shape (layered 2D arrays hold <= 2048 layers of <= 32768^2, "
@@ -47,6 +101,11 @@ extern "C" int xvr_volume_create(int D0, int D1, int D2, void** out) {
   vt->D0 = D0;
   vt->D1 = D1;
   vt->D2 = D2;
+  vt->bbox = nullptr;
+  vt->occ = nullptr;
+  vt->nb0 = (D0 + xvr::OCC_BRICK - 1) / xvr::OCC_BRICK;
+  vt->nb1 = (D1 + xvr::OCC_BRICK - 1) / xvr::OCC_BRICK;
+  vt->nb2 = (D2 + xvr::OCC_BRICK - 1) / xvr::OCC_BRICK;
   cudaChannelFormatDesc desc = cudaCreateChannelDesc<float>();
   cudaError_t e = cudaMalloc3DArray(&vt->array, &desc, make_cudaExtent(D2, D1, D0 + 2), cudaArrayLayered);
   if (e == cudaSuccess) {  // zero the two padding layers (0 and D0 + 1) once; uploads never touch them
@@ -76,6 +135,21 @@ extern "C" int xvr_volume_create(int D0, int D1, int D2, void** out) {
     td.normalizedCoords = 0;
     e = cudaCreateTextureObject(&vt->tex, &rd, &td, nullptr);
     if (e != cudaSuccess) cudaFreeArray(vt->array);
+  }
+  if (e == cudaSuccess) {
+    e = cudaMalloc(&vt->bbox, 6 * sizeof(int));
+    if (e == cudaSuccess) {  // until the first upload: the whole volume
+      const int whole[6] = {0, 0, 0, D0 - 1, D1 - 1, D2 - 1};
+      e = cudaMemcpy(vt->bbox, whole, sizeof(whole), cudaMemcpyHostToDevice);
+    }
+    if (e == cudaSuccess) e = cudaMalloc(&vt->occ, (size_t)vt->nb0 * vt->nb1 * vt->nb2);
+    if (e == cudaSuccess) e = cudaMemset(vt->occ, 1, (size_t)vt->nb0 * vt->nb1 * vt->nb2);  // until the first upload
+    if (e != cudaSuccess) {
+      cudaDestroyTextureObject(vt->tex);
+      cudaFreeArray(vt->array);
+      if (vt->bbox) cudaFree(vt->bbox);
+      if (vt->occ) cudaFree(vt->occ);
+    }
   }
   if (e != cudaSuccess) {
     char msg[256];
@@ -109,6 +183,29 @@ extern "C" int xvr_volume_upload(void* handle, const float* volume, void* stream
     cudaGetLastError();
     return XVR_ERR_CUDA;
   }
+  xvr::volume_bbox_init_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(vt->bbox, vt->D0, vt->D1, vt->D2);
+  xvr::volume_bbox_kernel<<<dim3((vt->D1 + 7) / 8, vt->D0), 256, 0, (cudaStream_t)stream>>>(volume, vt->D1, vt->D2, vt->bbox);
+  int rc = xvr::check_launch("xvr_volume_upload/bbox");
+  if (rc) return rc;
+  xvr::volume_occupancy_kernel<<<vt->nb0 * vt->nb1 * vt->nb2, 256, 0, (cudaStream_t)stream>>>(
+      volume, vt->D0, vt->D1, vt->D2, vt->nb1, vt->nb2, vt->occ);
+  return xvr::check_launch("xvr_volume_upload/occupancy");
+}
+
+// The box of non-zero voxels the last upload found: bbox6 HOST int[6] = lo0 lo1 lo2 hi0 hi1 hi2 (synchronises `stream`).
+extern "C" int xvr_volume_bbox(void* handle, int* bbox6, void* stream) {
+  xvr::VolumeTexture* vt = (xvr::VolumeTexture*)handle;
+  if (!vt || !bbox6) {
+    xvr::set_last_error("xvr_volume_bbox: null argument");
+    return XVR_ERR_INVALID;
+  }
+  cudaError_t e = cudaMemcpyAsync(bbox6, vt->bbox, 6 * sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
+  if (e != cudaSuccess) {
+    xvr::set_last_error(cudaGetErrorString(e));
+    cudaGetLastError();
+    return XVR_ERR_CUDA;
+  }
   return XVR_OK;
 }
 
@@ -117,6 +214,8 @@ extern "C" int xvr_volume_destroy(void* handle) {
   if (!vt) return XVR_OK;
   cudaDestroyTextureObject(vt->tex);
   cudaFreeArray(vt->array);
+  if (vt->bbox) cudaFree(vt->bbox);
+  if (vt->occ) cudaFree(vt->occ);
   delete vt;
   return XVR_OK;
 }

@@ -15,8 +15,9 @@
 #define XVR_OPT_KSPLIT_MASK 0x7        // 0: automatic, 1..4: 1/2/4/8 lanes share one ray (trilinear forward)
 #define XVR_OPT_SIDDON_WALK 0x10       // Siddon: voxel indices from the integer walk where its certificate holds
 #define XVR_OPT_VOLGRAD_GATHER 0x20    // dL/dvolume: voxel-centric gather instead of the brick-local scatter
+#define XVR_OPT_NO_TRIM 0x40           // trilinear: march all n_points samples even outside the box of non-zero voxels
 #define XVR_OPT_SIDDON_TOL_SHIFT 8     // bits 8..11, test hook: certificate tolerance 0: x1, 1: always exact, 2..4: x1/2, 1/4, 1/8
-#define XVR_OPT_KNOWN 0xF37
+#define XVR_OPT_KNOWN 0xF77
 
 namespace xvr {
 
@@ -28,7 +29,12 @@ struct Vol {
   int D0, D1, D2;
   int s0, s1;  // element strides of axis 0 / 1 (D1*D2, D2)
   cudaTextureObject_t tex;  // optional layered-2D copy: layer = axis 0, height = axis 1, width = axis 2
+  const int* __restrict__ bbox;  // optional DEVICE int[6]: first / last index of a non-zero voxel per axis (lo0 lo1 lo2 hi0 hi1 hi2)
+  const uint8_t* __restrict__ occ;  // optional occupancy of OCC_BRICK^3 bricks, (nb0,nb1,nb2): 1 if the brick grown by two
+  int nb0, nb1, nb2;                // voxels holds a non-zero voxel
 };
+
+constexpr int OCC_BRICK = 16;
 
 // Opaque handle behind xvr_volume_* (include/xvr_b200.h): a block-linear layered array + point-sampled texture.
 // The array has D0 + 2 layers: volume layer x lives in array layer x + 1, array layers 0 and D0 + 1 are zero, so
@@ -37,6 +43,9 @@ struct VolumeTexture {
   cudaArray_t array;
   cudaTextureObject_t tex;
   int D0, D1, D2;
+  int* bbox;  // DEVICE int[6], refreshed by every upload: the box of the volume's non-zero voxels (empty: lo = D, hi = -1)
+  uint8_t* occ;  // DEVICE (nb0,nb1,nb2) brick occupancy, refreshed by every upload
+  int nb0, nb1, nb2;
 };
 
 // The 2x2 (axis1, axis2) footprint around texel-corner (u, v) of one layer in a single TEX instruction.

@@ -65,6 +65,97 @@ __device__ __forceinline__ bool misses_padded_box(const float s[3], const float 
   return !(r.amin < r.amax);
 }
 
+// Empty-space trimming.  `bbox` = first / last index of a non-zero voxel per axis.  A sample at position x reads the
+// voxels floor(x), floor(x) + 1 on every axis: all 8 corners are zero -- value 0, gradient 0, an exact no-op for every
+// running sum -- unless lo - 1 < x < hi + 1 holds on all three axes.  Narrows the sample range [kb, ke) of a ray to the
+// samples that can lie inside that open box, with two samples of margin ALONG the ray for the rounding of alpha_k and
+// one more voxel ACROSS it (the box tested is (lo - 2, hi + 2): a ray that runs along a face of the box within rounding
+// must not be classified by the slab test on one side and sampled on the other).  Margin samples are marched as usual
+// and add their zeros: the rendered image and the Jacobian are bit-identical to the untrimmed march.
+__device__ __forceinline__ void trim_to_nonzero_box(const int* __restrict__ bbox, const float s[3], const float d[3],
+                                                    float amin, float span, int np, int& kb, int& ke) {
+  if (!(span > 0.f)) return;  // rays marched "backwards" through the padding: rare, left alone
+  float tin = -INFINITY, tout = INFINITY;
+  bool none = false;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const float lo = (float)(__ldg(bbox + a) - 2), hi = (float)(__ldg(bbox + 3 + a) + 2);
+    if (d[a] != 0.f) {
+      const float a0 = (lo - s[a]) / d[a], a1 = (hi - s[a]) / d[a];
+      tin = fmaxf(tin, fminf(a0, a1));
+      tout = fminf(tout, fmaxf(a0, a1));
+    } else if (!(s[a] > lo && s[a] < hi)) {
+      none = true;
+    }
+  }
+  if (none || !(tin <= tout)) {
+    ke = kb;
+    return;
+  }
+  const float sc = (float)(np - 1) / span;
+  const float kin = fminf(fmaxf((tin - amin) * sc, -4.f), (float)np + 4.f);
+  const float kout = fminf(fmaxf((tout - amin) * sc, -4.f), (float)np + 4.f);
+  kb = max(kb, (int)floorf(kin) - 2);
+  ke = min(ke, (int)ceilf(kout) + 3);
+  if (ke < kb) ke = kb;
+}
+
+// Second stage of the trimming: walk the ray through the occupancy grid of OCC_BRICK^3 bricks (3-D DDA) between alpha
+// a_lo and a_hi and narrow [kb, ke) to the samples between the entry into the first occupied brick and the exit from
+// the last one.  A brick counts as occupied if, grown by TWO voxels, it holds a non-zero voxel: a sample whose cell lies
+// in an unoccupied brick has 8 zero corners (one voxel of growth), even if the walk and the sample position disagree by
+// rounding about which side of a brick face a grazing ray is on (the second voxel); two samples of margin along the
+// ray cover the rounding of the entry / exit alphas.  (Empty bricks BETWEEN occupied ones are still marched.)
+__device__ __forceinline__ void trim_to_occupied_bricks(const Vol& v, const float s[3], const float d[3], float amin,
+                                                        float span, int np, int& kb, int& ke) {
+  if (!(span > 0.f) || ke <= kb) return;
+  const float lstep = 1.0f / (float)(np - 1);
+  // alpha of the first / last sample still in the range
+  const float a_lo = fmaf(lstep * (float)kb, span, amin), a_hi = fmaf(lstep * (float)(ke - 1), span, amin);
+  const float inv = 1.0f / (float)OCC_BRICK;
+  const int nb[3] = {v.nb0, v.nb1, v.nb2};
+  int c[3], stp[3];
+  float tmax[3], tdel[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const float pos = fmaf(a_lo, d[a], s[a]);
+    c[a] = (int)floorf(pos * inv);
+    stp[a] = d[a] > 0.f ? 1 : -1;
+    if (d[a] != 0.f) {
+      tdel[a] = fabsf((float)OCC_BRICK / d[a]);
+      tmax[a] = ((float)((c[a] + (d[a] > 0.f ? 1 : 0)) * OCC_BRICK) - s[a]) / d[a];
+    } else {
+      tdel[a] = INFINITY;
+      tmax[a] = INFINITY;
+    }
+  }
+  float t_cur = a_lo, first = INFINITY, last = -INFINITY;
+  const int max_steps = nb[0] + nb[1] + nb[2] + 4;
+  for (int it = 0; it < max_steps; ++it) {
+    const int b0 = min(max(c[0], 0), nb[0] - 1), b1 = min(max(c[1], 0), nb[1] - 1), b2 = min(max(c[2], 0), nb[2] - 1);
+    const float t_exit = fminf(fminf(tmax[0], tmax[1]), tmax[2]);
+    if (__ldg(v.occ + ((int64_t)b0 * nb[1] + b1) * nb[2] + b2)) {
+      first = fminf(first, t_cur);
+      last = fminf(t_exit, a_hi);
+    }
+    if (!(t_exit < a_hi)) break;
+    if (tmax[0] <= tmax[1] && tmax[0] <= tmax[2]) { c[0] += stp[0]; tmax[0] += tdel[0]; }
+    else if (tmax[1] <= tmax[2]) { c[1] += stp[1]; tmax[1] += tdel[1]; }
+    else { c[2] += stp[2]; tmax[2] += tdel[2]; }
+    t_cur = t_exit;
+  }
+  if (!(first <= last)) {
+    ke = kb;
+    return;
+  }
+  const float sc = (float)(np - 1) / span;
+  const float kin = fminf(fmaxf((first - amin) * sc, -4.f), (float)np + 4.f);
+  const float kout = fminf(fmaxf((last - amin) * sc, -4.f), (float)np + 4.f);
+  kb = max(kb, (int)floorf(kin) - 2);
+  ke = min(ke, (int)ceilf(kout) + 3);
+  if (ke < kb) ke = kb;
+}
+
 template <bool JAC, bool LABELS, bool TEX>
 __global__ void __launch_bounds__(256, XVR_TRI_MIN_CTAS) trilinear_fwd_kernel(const TrilinearParams p) {
   extern __shared__ float chan_acc[];  // LABELS: [C][256]
@@ -106,7 +197,11 @@ __global__ void __launch_bounds__(256, XVR_TRI_MIN_CTAS) trilinear_fwd_kernel(co
 
   // this lane's slice of the samples (all of them unless several lanes share the ray)
   const int part = (tid & 31) >> (5 - ks);
-  const int kbeg = (int)(((int64_t)np * part) >> ks), kend = (int)(((int64_t)np * (part + 1)) >> ks);
+  int kbeg = (int)(((int64_t)np * part) >> ks), kend = (int)(((int64_t)np * (part + 1)) >> ks);
+  if (p.vol.bbox) {
+    trim_to_nonzero_box(p.vol.bbox, s, d, ar.amin, span, np, kbeg, kend);
+    trim_to_occupied_bricks(p.vol, s, d, ar.amin, span, np, kbeg, kend);
+  }
 
   if (live && !misses_padded_box(s, d, p.vol)) {
     const float lstep = 1.0f / (float)(np - 1);
@@ -463,6 +558,7 @@ static int fill_common(TrilinearParams& p, const float* volume, const void* volt
   p.vol.s0 = D1 * D2;
   p.vol.s1 = D2;
   p.vol.tex = 0;
+  p.vol.bbox = nullptr;
   if (voltex) {
     const VolumeTexture* vt = (const VolumeTexture*)voltex;
     if (vt->D0 != D0 || vt->D1 != D1 || vt->D2 != D2) {
@@ -470,6 +566,13 @@ static int fill_common(TrilinearParams& p, const float* volume, const void* volt
       return XVR_ERR_INVALID;
     }
     p.vol.tex = vt->tex;
+    if (!(opts & XVR_OPT_NO_TRIM)) {  // empty-space trimming: the handle knows where its non-zero voxels are
+      p.vol.bbox = vt->bbox;
+      p.vol.occ = vt->occ;
+      p.vol.nb0 = vt->nb0;
+      p.vol.nb1 = vt->nb1;
+      p.vol.nb2 = vt->nb2;
+    }
   }
   p.labels = labels;
   p.C = C;
@@ -649,6 +752,65 @@ extern "C" int xvr_trilinear_drr_fwd(const float* volume, const void* voltex, in
     k<<<(unsigned)grid, 256, 0, st>>>(p);
   }
   return check_launch("xvr_trilinear_drr_fwd");
+}
+
+namespace xvr {
+__global__ void __launch_bounds__(256) trilinear_count_kernel(const TrilinearParams p, unsigned long long* counter) {
+  const int64_t ray = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  unsigned long long mine = 0;
+  if (ray < (int64_t)p.B * p.N) {
+    const int b = (int)(ray / p.N), n = (int)(ray - (int64_t)b * p.N);
+    float s[3], d[3], L;
+    generate_ray(p.geom, b, n, p.eps, s, d, L);
+    const float lo[3] = {0.f, 0.f, 0.f};
+    const float hi[3] = {(float)(p.vol.D0 - 1), (float)(p.vol.D1 - 1), (float)(p.vol.D2 - 1)};
+    const AlphaRange ar = alpha_range(s, d, lo, hi);
+    if (!misses_padded_box(s, d, p.vol)) {
+      int kb = 0, ke = p.n_points;
+      if (p.vol.bbox) {
+        trim_to_nonzero_box(p.vol.bbox, s, d, ar.amin, ar.amax - ar.amin, p.n_points, kb, ke);
+        trim_to_occupied_bricks(p.vol, s, d, ar.amin, ar.amax - ar.amin, p.n_points, kb, ke);
+      }
+      mine = (unsigned long long)(ke - kb);
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+  if ((threadIdx.x & 31) == 0 && mine) atomicAdd(counter, mine);
+}
+}  // namespace xvr
+
+// Number of samples xvr_trilinear_drr_fwd marches for this batch (bench.py: the executed share under empty-space
+// trimming; rays that miss the padded volume march none).  counter: DEVICE unsigned long long the caller zeroes.
+extern "C" int xvr_trilinear_drr_count(const void* voltex, int D0, int D1, int D2, const float* cam2vox,
+                                       const float* cam2world, const float* det9, int B, int det_h, int det_w,
+                                       int n_points, float eps, unsigned long long* counter, int opts, void* stream) {
+  if (!counter || B <= 0 || det_h <= 0 || det_w <= 0 || D0 < 2 || D1 < 2 || D2 < 2 || n_points < 2 ||
+      (opts & ~XVR_OPT_KNOWN)) {
+    set_last_error("xvr_trilinear_drr_count: invalid argument");
+    return XVR_ERR_INVALID;
+  }
+  TrilinearParams p = {};
+  p.fused = true;
+  int rc = fill_geom(p.geom, cam2vox, cam2world, det9, det_w);
+  if (rc) return rc;
+  p.vol.D0 = D0;
+  p.vol.D1 = D1;
+  p.vol.D2 = D2;
+  if (voltex && !(opts & XVR_OPT_NO_TRIM)) {
+    const VolumeTexture* vt = (const VolumeTexture*)voltex;
+    p.vol.bbox = vt->bbox;
+    p.vol.occ = vt->occ;
+    p.vol.nb0 = vt->nb0;
+    p.vol.nb1 = vt->nb1;
+    p.vol.nb2 = vt->nb2;
+  }
+  p.B = B;
+  p.N = det_h * det_w;
+  p.n_points = n_points;
+  p.eps = eps;
+  const int64_t rays = (int64_t)B * p.N;
+  trilinear_count_kernel<<<(unsigned)((rays + 255) / 256), 256, 0, (cudaStream_t)stream>>>(p, counter);
+  return check_launch("xvr_trilinear_drr_count");
 }
 
 // Backward of any fused DRR forward that saved its per-ray Jacobian: gG (B,3,4) = dL/d(cam2vox).
