@@ -157,20 +157,21 @@ def workload_text(cfg):
             f"detector, {how}, fwd + bwd w.r.t. 6-DoF pose")
 
 
-def siddon_segment_count(drr, rot, xyz, chunk=8):
+def siddon_segment_count(drr, rot, xyz, chunk=8, trim=False):
     """Total number of traversed segments of the batch (the Siddon algorithmic-bytes figure of SURVEY 8(d)), counted
     by the traversal kernel itself in count-only mode on materialised rays, a few poses at a time."""
     import xvr_b200
     from xvr_b200._lib import call, opts_word, ptr, stream
 
     total = 0
+    handle = drr.renderer._texture.get(drr.density) if trim else None  # occupancy: the trimmed traversal
     for i in range(0, rot.shape[0], chunk):
         pose = xvr_b200.convert(rot[i:i + chunk], xyz[i:i + chunk], parameterization="euler_angles", convention="ZXY")
         source, target = drr.detector(pose, None)
         source, target = drr.affine_inverse(source).contiguous(), drr.affine_inverse(target).contiguous()
         B, N, _ = target.shape
         cnt = torch.zeros(B, N, dtype=torch.int32, device=target.device)
-        call("xvr_siddon_trace", ptr(drr.density), *drr.density.shape, ptr(source), ptr(target), B, N,
+        call("xvr_siddon_trace", ptr(drr.density), handle, *drr.density.shape, ptr(source), ptr(target), B, N,
              float(drr.renderer.voxel_shift), float(drr.renderer.eps), 0, None, None, ptr(cnt), opts_word(), stream())
         total += int(cnt.sum(dtype=torch.int64).item())
     return total
@@ -306,6 +307,13 @@ def run_config(name, steps, warmup, rank, world, device, with_clocks=True):
                 call("xvr_trilinear_drr_count", handle, *drr.density.shape, ptr(cam2vox), ptr(cam2world), det9, B, H, W,
                      N_POINTS, float(drr.renderer.eps), ptr(counter), opts_word(), stream())
             counts.append(int(counter.item()))
+    else:
+        import ctypes
+
+        from xvr_b200._lib import call, options, stream
+        handle = drr.renderer._texture.get(drr.density)
+        counts = [siddon_segment_count(drr, rot_d, xyz_d, trim=True), siddon_segment_count(drr, rot_d, xyz_d)]
+    if True:
         bbox = (ctypes.c_int * 6)()
         call("xvr_volume_bbox", handle, bbox, stream())
         k = max(3, min(steps, 10))
@@ -322,10 +330,18 @@ def run_config(name, steps, warmup, rank, world, device, with_clocks=True):
         t_off = torch.tensor([t0.elapsed_time(t1)], device=device, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(t_off, op=dist.ReduceOp.MAX)
-        trimming = {"what": "samples whose 8 corners lie outside the box of the volume's non-zero voxels are skipped "
-                            "(exact zeros for every sum: images and Jacobians bit-identical to the full march, "
-                            "tests/test_trilinear_gpu.py::test_empty_space_trimming_is_bit_identical)",
-                    "nonzero_box": list(bbox), "samples_in_volume": counts[1], "samples_marched": counts[0],
+        unit = "samples" if name == "trilinear" else "segments"
+        what = ("samples whose 8 corners lie outside the box of the volume's non-zero voxels / before the first and "
+                "after the last occupied 16^3 brick on the ray are skipped (exact zeros for every sum: images and "
+                "Jacobians bit-identical to the full march, "
+                "tests/test_trilinear_gpu.py::test_empty_space_trimming_is_bit_identical)" if name == "trilinear" else
+                "plane crossings before a ray enters the first occupied 16^3 brick and after it leaves the last one are "
+                "dropped (the segments are air: exact zeros for the line integral and the Jacobian sums, images and "
+                "Jacobians bit-identical to the full traversal, "
+                "tests/test_siddon_gpu.py::test_empty_space_trimming_is_bit_identical, "
+                "::test_trimmed_traversal_is_a_run_of_the_full_one_and_drops_only_air)")
+        trimming = {"what": what,
+                    "nonzero_box": list(bbox), f"{unit}_in_volume": counts[1], f"{unit}_marched": counts[0],
                     "marched_fraction": counts[0] / max(1, counts[1]),
                     "value_without_trimming": world * B * k / (t_off.item() * 1e-3),
                     "ms_per_step_without_trimming": t_off.item() / k}
@@ -413,10 +429,11 @@ def run_config(name, steps, warmup, rank, world, device, with_clocks=True):
         two_pass = 2.0
     else:
         entry = "xvr_siddon_drr_fwd"
-        n_seg = siddon_segment_count(drr, rot_d, xyz_d)
+        n_seg = trimming["segments_marched"]  # the trimmed ones are never fetched: not credited
         alg = n_seg * 4 + B * H * W * 4  # one 4-byte voxel per traversed segment + the output pixel
-        alg_note = (f"sum over rays of (n_seg*4+4): {n_seg} traversed segments in the batch "
-                    f"({n_seg / (B * H * W):.1f} per ray), counted by xvr_siddon_trace")
+        alg_note = (f"sum over rays of (n_seg*4+4): {n_seg} WALKED segments in the batch ({n_seg / (B * H * W):.1f} per "
+                    f"ray; {trimming['segments_in_volume']} before the empty-space trimming), counted by "
+                    "xvr_siddon_trace with the same occupancy handle")
         kernel = "siddon_fwd_kernel<JAC=true> (traversal + per-ray pose Jacobian in one pass)"
         two_pass = 2.0
     k_ms = kernel_ms.get(entry, [])

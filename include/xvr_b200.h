@@ -41,6 +41,9 @@ long long xvr_launch_count(void);
  * Replaces nothing in the reference (which samples with F.grid_sample on the linear tensor); it is the HBM layout
  * the trilinear kernels prefer.  Optional: pass NULL as `voltex` below to gather from the linear volume. */
 int xvr_volume_create(int D0, int D1, int D2, void** handle_out);
+/* the same handle without the texture copy (no D0 <= 2046 limit, no second copy of the volume): only the non-zero box
+ * and the brick occupancy that xvr_volume_upload records -- what the Siddon entries take as `occupancy` */
+int xvr_occupancy_create(int D0, int D1, int D2, void** handle_out);
 int xvr_volume_upload(void* handle, const float* volume, void* stream);
 int xvr_volume_destroy(void* handle);
 /* Every upload also records the box of the volume's NON-ZERO voxels (transform_hu_to_density maps air to exactly 0, and CT
@@ -123,10 +126,14 @@ int xvr_siddon_rays_fwd(const float* volume, int D0, int D1, int D2, const uint8
                         float* out, float* jac, int opts, void* stream);
 /* fused Siddon DRR = diffdrr.drr.DRR.forward with renderer="siddon" (registrar/base.py:249, trainer.py:283-289 with
  * --renderer siddon): rays generated in-kernel as in xvr_trilinear_drr_fwd, out (B,1,H*W), jac (B,7,H*W) or NULL;
- * backward = xvr_drr_jac_bwd */
-int xvr_siddon_drr_fwd(const float* volume, int D0, int D1, int D2, const float* cam2vox, const float* cam2world,
-                       const float* det9, int B, int det_h, int det_w, float voxel_shift, float eps, int lane_w_log2,
-                       int cta_w_log2, float* out, float* jac, int opts, void* stream);
+ * backward = xvr_drr_jac_bwd.
+ * `occupancy` (NULL = none): a handle of xvr_occupancy_create (or xvr_volume_create) the volume was uploaded to.  With
+ * it every ray's plane crossings are restricted to the stretch from its entry into the first occupied 16^3 brick to its
+ * exit from the last one: the segments dropped are air (value exactly 0), i.e. exact zeros for the line integral and for
+ * the Jacobian sums, so image and Jacobian are bit-identical to the full traversal (XVR_OPT_NO_TRIM switches it off). */
+int xvr_siddon_drr_fwd(const float* volume, const void* occupancy, int D0, int D1, int D2, const float* cam2vox,
+                       const float* cam2world, const float* det9, int B, int det_h, int det_w, float voxel_shift,
+                       float eps, int lane_w_log2, int cta_w_log2, float* out, float* jac, int opts, void* stream);
 int xvr_siddon_rays_bwd(const float* volume, int D0, int D1, int D2, const uint8_t* labels, int C,
                         const float* source, const float* target, const float* raylen, int B, int N,
                         float voxel_shift, float eps, int det_h, int det_w, int lane_w_log2, int cta_w_log2,
@@ -142,9 +149,9 @@ int xvr_siddon_drr_bwd_volume(const float* cam2vox, const float* vox2cam, const 
                               int D1, int D2, float* gvol, int accumulate, int opts, void* stream);
 /* the traversal itself (test hook, and bench.py's segment count): idx/seg (B,N,trace_max), count (B,N);
  * trace_max = 0 with idx = seg = NULL writes the per-ray segment counts only */
-int xvr_siddon_trace(const float* volume, int D0, int D1, int D2, const float* source, const float* target, int B,
-                     int N, float voxel_shift, float eps, int trace_max, int32_t* idx, float* seg, int32_t* count,
-                     int opts, void* stream);
+int xvr_siddon_trace(const float* volume, const void* occupancy /* nullable, as in xvr_siddon_drr_fwd */, int D0, int D1,
+                     int D2, const float* source, const float* target, int B, int N, float voxel_shift, float eps,
+                     int trace_max, int32_t* idx, float* seg, int32_t* count, int opts, void* stream);
 /* Voxel index of a segment: the certified evaluation of the midpoint (default).  With XVR_OPT_SIDDON_WALK the forward
  * (without label channels) and trace kernels take it from an integer walk (+-stride at every plane crossing) whenever
  * min_a |d_a| * segment length / 2 exceeds the rounding budget of the certified evaluation -- provably the same index

@@ -111,7 +111,7 @@ def section_siddon():
     cnt = torch.zeros(Bs, N, dtype=torch.int32, device=dev)
     idx = torch.zeros(Bs, N, 1, dtype=torch.int32, device=dev)
     seg = torch.zeros(Bs, N, 1, device=dev)
-    _lib.call("xvr_siddon_trace", _lib.ptr(sdrr.density), *sdrr.density.shape, _lib.ptr(src), _lib.ptr(tgt), Bs, N, 0.5, 1e-8, 1,
+    _lib.call("xvr_siddon_trace", _lib.ptr(sdrr.density), None, *sdrr.density.shape, _lib.ptr(src), _lib.ptr(tgt), Bs, N, 0.5, 1e-8, 1,
               _lib.ptr(idx), _lib.ptr(seg), _lib.ptr(cnt), _lib.opts_word(), _lib.stream())
     nseg = cnt.sum().item()
     print(json.dumps({"siddon_mean_segments_per_ray": nseg / (Bs * N)}))

@@ -25,7 +25,7 @@ for seed in (0, 1):
         seg = torch.zeros(B, N, M, device=dev)
         cnt = torch.zeros(B, N, dtype=torch.int32, device=dev)
         with options(siddon_tol=scale):  # per-call option word (include/xvr_b200.h XVR_OPT_SIDDON_TOL)
-            call("xvr_siddon_trace", ptr(drr.density), *drr.density.shape, ptr(src), ptr(tgt), B, N, 0.5, 1e-8, M, ptr(idx),
+            call("xvr_siddon_trace", ptr(drr.density), None, *drr.density.shape, ptr(src), ptr(tgt), B, N, 0.5, 1e-8, M, ptr(idx),
                  ptr(seg), ptr(cnt), opts_word(), stream())
         return idx, cnt
 

@@ -42,7 +42,7 @@ def test_library_exports_every_declared_symbol():
     assert len(protos) >= 19
     for name in protos:
         assert hasattr(handle, name), f"{name} declared in include/xvr_b200.h but not exported"
-    assert handle.xvr_abi_version() == 2
+    assert handle.xvr_abi_version() == 3
 
 
 def test_bindings_match_header_arity():
@@ -70,9 +70,9 @@ def test_invalid_arguments_return_error_codes_not_crashes():
                                             None) == -1
     assert b"xvr_trilinear_drr_fwd_staged" in lib.xvr_last_error()
     # per-call options: unknown bits and out-of-range fields are invalid arguments, checked before any device work
-    assert lib.xvr_siddon_drr_fwd(None, 8, 8, 8, None, None, None, 1, 16, 16, 0.5, 1e-8, 0, 3, None, None, 0, None) == -1
+    assert lib.xvr_siddon_drr_fwd(None, None, 8, 8, 8, None, None, None, 1, 16, 16, 0.5, 1e-8, 0, 3, None, None, 0, None) == -1
     assert b"xvr_siddon_drr_fwd" in lib.xvr_last_error()
-    assert lib.xvr_abi_version() == 2
+    assert lib.xvr_abi_version() == 3
 
 
 def test_product_never_imports_the_oracle():

@@ -25,12 +25,12 @@ def _rays(drr, rot, xyz):
     return drr.affine_inverse(source).contiguous(), drr.affine_inverse(target).contiguous(), raylen
 
 
-def _trace(vol, source, target, shift, max_seg):
+def _trace(vol, source, target, shift, max_seg, occupancy=None):
     B, N, _ = target.shape
     idx = torch.full((B, N, max_seg), -2, dtype=torch.int32, device=vol.device)
     seg = torch.zeros(B, N, max_seg, device=vol.device)
     cnt = torch.zeros(B, N, dtype=torch.int32, device=vol.device)
-    call("xvr_siddon_trace", ptr(vol), *vol.shape, ptr(source), ptr(target), B, N, shift, 1e-8, max_seg, ptr(idx),
+    call("xvr_siddon_trace", ptr(vol), occupancy, *vol.shape, ptr(source), ptr(target), B, N, shift, 1e-8, max_seg, ptr(idx),
          ptr(seg), ptr(cnt), opts_word(), stream())
     return idx, seg, cnt
 
@@ -252,3 +252,94 @@ def test_siddon_pose_gradient_against_the_fp64_arbiter(cuda, monkeypatch):
         ours = torch.cat([r.grad, x.grad], 1).double()
         print(f"siddon pose gradient vs fp64 arbiter (fused={fused}): kernel {err(ours):.2e}, fp32 oracle {err(g32):.2e}")
         assert err(ours) < max(floor, 3 * err(g32)), (fused, err(ours), err(g32))
+
+
+# ------------------------------------------------------------------------------------------ empty-space trimming
+def _scene(cuda, scene):
+    from tests.test_zz_full_size_gpu import EDGE_ROT, EDGE_XYZ
+
+    drr = make_drr(64, 40, renderer="siddon")
+    rot, xyz = pose_params(3, seed=17)
+    if scene == "blob":
+        vol = torch.zeros_like(drr.density)
+        vol[20:27, 40:44, 9:30] = torch.rand(7, 4, 21, device=cuda) + 0.1
+        drr.density = vol
+    elif scene == "two_blobs":  # air BETWEEN occupied bricks is walked, air before / after is not
+        vol = torch.zeros_like(drr.density)
+        vol[3:9, 5:30, 40:60] = torch.rand(6, 25, 20, device=cuda) + 0.1
+        vol[50:62, 33:35, 1:20] = torch.rand(12, 2, 19, device=cuda) + 0.1
+        drr.density = vol
+    elif scene == "dense":
+        drr.density = torch.rand_like(drr.density) + 0.5
+    elif scene == "zeros":
+        drr.density = torch.zeros_like(drr.density)
+    elif scene == "edge":
+        rot, xyz = torch.tensor(EDGE_ROT, device=cuda), torch.tensor(EDGE_XYZ, device=cuda)
+    return drr, rot, xyz
+
+
+SCENES = ["phantom", "blob", "two_blobs", "dense", "zeros", "edge"]
+
+
+@pytest.mark.parametrize("scene", SCENES)
+def test_empty_space_trimming_is_bit_identical(cuda, scene):
+    """xvr_siddon_drr_fwd with an occupancy handle drops the plane crossings before a ray enters the first occupied
+    brick and after it leaves the last one: images and pose gradients equal the full traversal bit for bit."""
+    from xvr_b200._lib import options
+
+    drr, rot, xyz = _scene(cuda, scene)
+    outs = []
+    for trim in (True, False):
+        with options(trim=trim):
+            r, x = rot.clone().requires_grad_(), xyz.clone().requires_grad_()
+            img = drr(xvr_b200.convert(r, x, parameterization="euler_angles", convention="ZXY"))
+            w = torch.rand(img.shape, generator=torch.Generator().manual_seed(1)).to(cuda)
+            (img * w).sum().backward()
+            outs.append((img.detach().clone(), r.grad.clone(), x.grad.clone()))
+    for u, v in zip(*outs):
+        assert torch.equal(u, v)
+    if scene in ("phantom", "blob", "two_blobs"):
+        assert outs[0][0].abs().sum() > 0
+
+
+@pytest.mark.parametrize("scene", SCENES)
+def test_trimmed_traversal_is_a_run_of_the_full_one_and_drops_only_air(cuda, scene):
+    """The traversal itself, with and without the occupancy handle: every ray's trimmed (voxel index, segment length)
+    list is a CONTIGUOUS RUN of its full list, bit for bit, and every segment dropped lies in a voxel whose value is
+    exactly 0 (or outside the volume) -- the property the bit-identity of images and Jacobians rests on, checked
+    without relying on sums."""
+    drr, rot, xyz = _scene(cuda, scene)
+    vol = drr.density.contiguous()
+    source, target, _ = _rays(drr, rot, xyz)
+    handle = drr.renderer._texture.get(vol)
+    assert handle is not None
+    M = 3 * 66
+    idx_f, seg_f, cnt_f = _trace(vol, source, target, 0.5, M)
+    idx_t, seg_t, cnt_t = _trace(vol, source, target, 0.5, M, occupancy=handle)
+    assert int(cnt_f.max()) <= M and (cnt_t <= cnt_f).all()
+    col = torch.arange(M, device=cuda)[None, None]
+    live_t = col < cnt_t[..., None]
+    found = cnt_t == 0
+    offset = torch.zeros_like(cnt_t)
+    for o in range(M):
+        if bool(found.all()):
+            break
+        shifted_idx = torch.roll(idx_f, -o, dims=-1)
+        shifted_seg = torch.roll(seg_f, -o, dims=-1)
+        fits = (cnt_t + o) <= cnt_f
+        same = ((shifted_idx == idx_t) & (shifted_seg == seg_t)) | ~live_t
+        hit = fits & same.all(-1) & ~found
+        offset = torch.where(hit, torch.full_like(offset, o), offset)
+        found |= hit
+    assert bool(found.all()), f"{int((~found).sum())} trimmed rays are not a run of the full traversal"
+    value = torch.where(idx_f >= 0, vol.flatten()[idx_f.clamp_min(0).long()], torch.zeros_like(seg_f))
+    live_f = col < cnt_f[..., None]
+    kept = (col >= offset[..., None]) & (col < (offset + cnt_t)[..., None])
+    dropped = live_f & ~kept
+    assert bool((value[dropped] == 0).all())
+    share = cnt_t.sum().item() / max(1, cnt_f.sum().item())
+    print(f"siddon trimming, {scene}: {share:.3f} of the segments walked")
+    if scene in ("blob", "two_blobs", "zeros"):
+        assert share < 0.6
+    if scene == "dense":
+        assert share == 1.0

@@ -273,7 +273,7 @@ def test_config5_traversal_is_bit_exact_on_a_ray_sample(config5):
     idx = torch.full((B, N, M + 8), -2, dtype=torch.int32, device=target.device)
     seg = torch.zeros(B, N, M + 8, device=target.device)
     cnt = torch.zeros(B, N, dtype=torch.int32, device=target.device)
-    call("xvr_siddon_trace", ptr(drr.density), *shape, ptr(source), ptr(target), B, N, 0.5, 1e-8, M + 8, ptr(idx),
+    call("xvr_siddon_trace", ptr(drr.density), None, *shape, ptr(source), ptr(target), B, N, 0.5, 1e-8, M + 8, ptr(idx),
          ptr(seg), ptr(cnt), 0, stream())
     assert torch.equal(cnt, ref_cnt.to(torch.int32))
     live = torch.arange(M, device=target.device)[None, None] < ref_cnt[..., None]

@@ -19,6 +19,7 @@ _SIGNATURES = {
     "xvr_last_error": ([], ctypes.c_char_p),
     "xvr_launch_count": ([], c_int64),
     "xvr_volume_create": ([c_int, c_int, c_int, ctypes.POINTER(c_void_p)], c_int),
+    "xvr_occupancy_create": ([c_int, c_int, c_int, ctypes.POINTER(c_void_p)], c_int),
     "xvr_volume_upload": ([P, P, P], c_int),
     "xvr_volume_destroy": ([P], c_int),
     "xvr_volume_bbox": ([P, ctypes.POINTER(c_int), P], c_int),
@@ -66,7 +67,7 @@ _SIGNATURES = {
         [P, c_int, c_int, c_int, P, c_int, P, P, P, c_int, c_int, c_float, c_float, c_int, c_int, c_int, c_int, P, P,
          c_int, P], c_int),
     "xvr_siddon_drr_fwd": (
-        [P, c_int, c_int, c_int, P, P, ctypes.POINTER(c_float), c_int, c_int, c_int, c_float, c_float, c_int, c_int, P,
+        [P, P, c_int, c_int, c_int, P, P, ctypes.POINTER(c_float), c_int, c_int, c_int, c_float, c_float, c_int, c_int, P,
          P, c_int, P], c_int),
     "xvr_siddon_rays_bwd": (
         [P, c_int, c_int, c_int, P, c_int, P, P, P, c_int, c_int, c_float, c_float, c_int, c_int, c_int, c_int, P, P,
@@ -76,7 +77,7 @@ _SIGNATURES = {
          P], c_int),
     "xvr_selftest_division": ([c_int, c_int, ctypes.c_uint, P, P], c_int),
     "xvr_siddon_trace": (
-        [P, c_int, c_int, c_int, P, P, c_int, c_int, c_float, c_float, c_int, P, P, P, c_int, P], c_int),
+        [P, P, c_int, c_int, c_int, P, P, c_int, c_int, c_float, c_float, c_int, P, P, P, c_int, P], c_int),
 }
 
 # ---- per-call kernel options (include/xvr_b200.h XVR_OPT_*).  The library itself keeps no mutable state: the

@@ -29,7 +29,7 @@ int check_launch(const char* what) {
 
 extern "C" const char* xvr_last_error(void) { return xvr::g_last_error; }
 
-extern "C" int xvr_abi_version(void) { return 2; }
+extern "C" int xvr_abi_version(void) { return 3; }
 
 // Number of kernels this library has launched since load (bench.py's gpu_launches evidence).
 extern "C" long long xvr_launch_count(void) { return xvr::g_launches; }
@@ -91,8 +91,16 @@ __global__ void __launch_bounds__(256) volume_occupancy_kernel(const float* __re
 }
 }  // namespace xvr
 
-extern "C" int xvr_volume_create(int D0, int D1, int D2, void** out) {
-  if (!out || D0 < 1 || D1 < 1 || D2 < 1 || D0 > 2046 || D1 > 32768 || D2 > 32768) {
+static int volume_create(int D0, int D1, int D2, void** out, bool with_texture);
+
+extern "C" int xvr_volume_create(int D0, int D1, int D2, void** out) { return volume_create(D0, D1, D2, out, true); }
+
+// The same handle without the texture copy (the Siddon renderer gathers from the linear volume and only wants the
+// occupancy the uploads record: no second copy of a 1.8 GB volume).
+extern "C" int xvr_occupancy_create(int D0, int D1, int D2, void** out) { return volume_create(D0, D1, D2, out, false); }
+
+static int volume_create(int D0, int D1, int D2, void** out, bool with_texture) {
+  if (!out || D0 < 1 || D1 < 1 || D2 < 1 || (with_texture && (D0 > 2046 || D1 > 32768 || D2 > 32768))) {
     xvr::set_last_error("xvr_volume_create: invalid shape (layered 2D arrays hold <= 2048 layers of <= 32768^2, "
                         "two of which are the zero padding)");
     return XVR_ERR_INVALID;
@@ -106,9 +114,12 @@ extern "C" int xvr_volume_create(int D0, int D1, int D2, void** out) {
   vt->nb0 = (D0 + xvr::OCC_BRICK - 1) / xvr::OCC_BRICK;
   vt->nb1 = (D1 + xvr::OCC_BRICK - 1) / xvr::OCC_BRICK;
   vt->nb2 = (D2 + xvr::OCC_BRICK - 1) / xvr::OCC_BRICK;
+  vt->array = nullptr;
+  vt->tex = 0;
   cudaChannelFormatDesc desc = cudaCreateChannelDesc<float>();
-  cudaError_t e = cudaMalloc3DArray(&vt->array, &desc, make_cudaExtent(D2, D1, D0 + 2), cudaArrayLayered);
-  if (e == cudaSuccess) {  // zero the two padding layers (0 and D0 + 1) once; uploads never touch them
+  cudaError_t e = with_texture ? cudaMalloc3DArray(&vt->array, &desc, make_cudaExtent(D2, D1, D0 + 2), cudaArrayLayered)
+                               : cudaSuccess;
+  if (e == cudaSuccess && with_texture) {  // zero the two padding layers (0 and D0 + 1) once; uploads never touch them
     float* zeros = nullptr;
     e = cudaMalloc(&zeros, (size_t)D1 * D2 * sizeof(float));
     if (e == cudaSuccess) e = cudaMemset(zeros, 0, (size_t)D1 * D2 * sizeof(float));
@@ -124,7 +135,7 @@ extern "C" int xvr_volume_create(int D0, int D1, int D2, void** out) {
     if (zeros) cudaFree(zeros);
     if (e != cudaSuccess) cudaFreeArray(vt->array);
   }
-  if (e == cudaSuccess) {
+  if (e == cudaSuccess && with_texture) {
     cudaResourceDesc rd = {};
     rd.resType = cudaResourceTypeArray;
     rd.res.array.array = vt->array;
@@ -145,8 +156,8 @@ extern "C" int xvr_volume_create(int D0, int D1, int D2, void** out) {
     if (e == cudaSuccess) e = cudaMalloc(&vt->occ, (size_t)vt->nb0 * vt->nb1 * vt->nb2);
     if (e == cudaSuccess) e = cudaMemset(vt->occ, 1, (size_t)vt->nb0 * vt->nb1 * vt->nb2);  // until the first upload
     if (e != cudaSuccess) {
-      cudaDestroyTextureObject(vt->tex);
-      cudaFreeArray(vt->array);
+      if (vt->tex) cudaDestroyTextureObject(vt->tex);
+      if (vt->array) cudaFreeArray(vt->array);
       if (vt->bbox) cudaFree(vt->bbox);
       if (vt->occ) cudaFree(vt->occ);
     }
@@ -169,13 +180,16 @@ extern "C" int xvr_volume_upload(void* handle, const float* volume, void* stream
     xvr::set_last_error("xvr_volume_upload: null argument");
     return XVR_ERR_INVALID;
   }
-  cudaMemcpy3DParms cp = {};
-  cp.srcPtr = make_cudaPitchedPtr((void*)volume, (size_t)vt->D2 * sizeof(float), vt->D2, vt->D1);
-  cp.dstArray = vt->array;
-  cp.dstPos = make_cudaPos(0, 0, 1);  // array layer 0 is zero padding
-  cp.extent = make_cudaExtent(vt->D2, vt->D1, vt->D0);
-  cp.kind = cudaMemcpyDeviceToDevice;
-  cudaError_t e = cudaMemcpy3DAsync(&cp, (cudaStream_t)stream);
+  cudaError_t e = cudaSuccess;
+  if (vt->array) {
+    cudaMemcpy3DParms cp = {};
+    cp.srcPtr = make_cudaPitchedPtr((void*)volume, (size_t)vt->D2 * sizeof(float), vt->D2, vt->D1);
+    cp.dstArray = vt->array;
+    cp.dstPos = make_cudaPos(0, 0, 1);  // array layer 0 is zero padding
+    cp.extent = make_cudaExtent(vt->D2, vt->D1, vt->D0);
+    cp.kind = cudaMemcpyDeviceToDevice;
+    e = cudaMemcpy3DAsync(&cp, (cudaStream_t)stream);
+  }
   if (e != cudaSuccess) {
     char msg[256];
     snprintf(msg, sizeof(msg), "xvr_volume_upload: %s", cudaGetErrorString(e));
@@ -212,8 +226,8 @@ extern "C" int xvr_volume_bbox(void* handle, int* bbox6, void* stream) {
 extern "C" int xvr_volume_destroy(void* handle) {
   xvr::VolumeTexture* vt = (xvr::VolumeTexture*)handle;
   if (!vt) return XVR_OK;
-  cudaDestroyTextureObject(vt->tex);
-  cudaFreeArray(vt->array);
+  if (vt->tex) cudaDestroyTextureObject(vt->tex);
+  if (vt->array) cudaFreeArray(vt->array);
   if (vt->bbox) cudaFree(vt->bbox);
   if (vt->occ) cudaFree(vt->occ);
   delete vt;

@@ -65,86 +65,16 @@ __device__ __forceinline__ bool misses_padded_box(const float s[3], const float 
   return !(r.amin < r.amax);
 }
 
-// Empty-space trimming.  `bbox` = first / last index of a non-zero voxel per axis.  A sample at position x reads the
-// voxels floor(x), floor(x) + 1 on every axis: all 8 corners are zero -- value 0, gradient 0, an exact no-op for every
-// running sum -- unless lo - 1 < x < hi + 1 holds on all three axes.  Narrows the sample range [kb, ke) of a ray to the
-// samples that can lie inside that open box, with two samples of margin ALONG the ray for the rounding of alpha_k and
-// one more voxel ACROSS it (the box tested is (lo - 2, hi + 2): a ray that runs along a face of the box within rounding
-// must not be classified by the slab test on one side and sampled on the other).  Margin samples are marched as usual
-// and add their zeros: the rendered image and the Jacobian are bit-identical to the untrimmed march.
-__device__ __forceinline__ void trim_to_nonzero_box(const int* __restrict__ bbox, const float s[3], const float d[3],
-                                                    float amin, float span, int np, int& kb, int& ke) {
-  if (!(span > 0.f)) return;  // rays marched "backwards" through the padding: rare, left alone
-  float tin = -INFINITY, tout = INFINITY;
-  bool none = false;
-#pragma unroll
-  for (int a = 0; a < 3; ++a) {
-    const float lo = (float)(__ldg(bbox + a) - 2), hi = (float)(__ldg(bbox + 3 + a) + 2);
-    if (d[a] != 0.f) {
-      const float a0 = (lo - s[a]) / d[a], a1 = (hi - s[a]) / d[a];
-      tin = fmaxf(tin, fminf(a0, a1));
-      tout = fminf(tout, fmaxf(a0, a1));
-    } else if (!(s[a] > lo && s[a] < hi)) {
-      none = true;
-    }
-  }
-  if (none || !(tin <= tout)) {
-    ke = kb;
-    return;
-  }
-  const float sc = (float)(np - 1) / span;
-  const float kin = fminf(fmaxf((tin - amin) * sc, -4.f), (float)np + 4.f);
-  const float kout = fminf(fmaxf((tout - amin) * sc, -4.f), (float)np + 4.f);
-  kb = max(kb, (int)floorf(kin) - 2);
-  ke = min(ke, (int)ceilf(kout) + 3);
-  if (ke < kb) ke = kb;
-}
-
-// Second stage of the trimming: walk the ray through the occupancy grid of OCC_BRICK^3 bricks (3-D DDA) between alpha
-// a_lo and a_hi and narrow [kb, ke) to the samples between the entry into the first occupied brick and the exit from
-// the last one.  A brick counts as occupied if, grown by TWO voxels, it holds a non-zero voxel: a sample whose cell lies
-// in an unoccupied brick has 8 zero corners (one voxel of growth), even if the walk and the sample position disagree by
-// rounding about which side of a brick face a grazing ray is on (the second voxel); two samples of margin along the
-// ray cover the rounding of the entry / exit alphas.  (Empty bricks BETWEEN occupied ones are still marched.)
-__device__ __forceinline__ void trim_to_occupied_bricks(const Vol& v, const float s[3], const float d[3], float amin,
-                                                        float span, int np, int& kb, int& ke) {
-  if (!(span > 0.f) || ke <= kb) return;
+// Empty-space trimming of a ray's sample range [kb, ke): the samples before the ray enters the occupied part of the
+// volume and after it leaves it have 8 zero corners -- value 0, gradient 0, an exact no-op for every running sum
+// (occupied_alpha_range, common.cuh).  Two samples of margin along the ray for the rounding of alpha_k; margin samples
+// are marched as usual and add their zeros: the rendered image and the Jacobian are bit-identical to the full march.
+__device__ __forceinline__ void trim_sample_range(const Vol& v, const float s[3], const float d[3], float amin,
+                                                  float span, int np, int& kb, int& ke) {
+  if (!(span > 0.f) || ke <= kb) return;  // rays marched "backwards" through the padding: rare, left alone
   const float lstep = 1.0f / (float)(np - 1);
-  // alpha of the first / last sample still in the range
-  const float a_lo = fmaf(lstep * (float)kb, span, amin), a_hi = fmaf(lstep * (float)(ke - 1), span, amin);
-  const float inv = 1.0f / (float)OCC_BRICK;
-  const int nb[3] = {v.nb0, v.nb1, v.nb2};
-  int c[3], stp[3];
-  float tmax[3], tdel[3];
-#pragma unroll
-  for (int a = 0; a < 3; ++a) {
-    const float pos = fmaf(a_lo, d[a], s[a]);
-    c[a] = (int)floorf(pos * inv);
-    stp[a] = d[a] > 0.f ? 1 : -1;
-    if (d[a] != 0.f) {
-      tdel[a] = fabsf((float)OCC_BRICK / d[a]);
-      tmax[a] = ((float)((c[a] + (d[a] > 0.f ? 1 : 0)) * OCC_BRICK) - s[a]) / d[a];
-    } else {
-      tdel[a] = INFINITY;
-      tmax[a] = INFINITY;
-    }
-  }
-  float t_cur = a_lo, first = INFINITY, last = -INFINITY;
-  const int max_steps = nb[0] + nb[1] + nb[2] + 4;
-  for (int it = 0; it < max_steps; ++it) {
-    const int b0 = min(max(c[0], 0), nb[0] - 1), b1 = min(max(c[1], 0), nb[1] - 1), b2 = min(max(c[2], 0), nb[2] - 1);
-    const float t_exit = fminf(fminf(tmax[0], tmax[1]), tmax[2]);
-    if (__ldg(v.occ + ((int64_t)b0 * nb[1] + b1) * nb[2] + b2)) {
-      first = fminf(first, t_cur);
-      last = fminf(t_exit, a_hi);
-    }
-    if (!(t_exit < a_hi)) break;
-    if (tmax[0] <= tmax[1] && tmax[0] <= tmax[2]) { c[0] += stp[0]; tmax[0] += tdel[0]; }
-    else if (tmax[1] <= tmax[2]) { c[1] += stp[1]; tmax[1] += tdel[1]; }
-    else { c[2] += stp[2]; tmax[2] += tdel[2]; }
-    t_cur = t_exit;
-  }
-  if (!(first <= last)) {
+  float first = fmaf(lstep * (float)kb, span, amin), last = fmaf(lstep * (float)(ke - 1), span, amin);
+  if (!occupied_alpha_range(v, s, d, first, last)) {
     ke = kb;
     return;
   }
@@ -198,10 +128,7 @@ __global__ void __launch_bounds__(256, XVR_TRI_MIN_CTAS) trilinear_fwd_kernel(co
   // this lane's slice of the samples (all of them unless several lanes share the ray)
   const int part = (tid & 31) >> (5 - ks);
   int kbeg = (int)(((int64_t)np * part) >> ks), kend = (int)(((int64_t)np * (part + 1)) >> ks);
-  if (p.vol.bbox) {
-    trim_to_nonzero_box(p.vol.bbox, s, d, ar.amin, span, np, kbeg, kend);
-    trim_to_occupied_bricks(p.vol, s, d, ar.amin, span, np, kbeg, kend);
-  }
+  if (p.vol.bbox) trim_sample_range(p.vol, s, d, ar.amin, span, np, kbeg, kend);
 
   if (live && !misses_padded_box(s, d, p.vol)) {
     const float lstep = 1.0f / (float)(np - 1);
@@ -767,10 +694,7 @@ __global__ void __launch_bounds__(256) trilinear_count_kernel(const TrilinearPar
     const AlphaRange ar = alpha_range(s, d, lo, hi);
     if (!misses_padded_box(s, d, p.vol)) {
       int kb = 0, ke = p.n_points;
-      if (p.vol.bbox) {
-        trim_to_nonzero_box(p.vol.bbox, s, d, ar.amin, ar.amax - ar.amin, p.n_points, kb, ke);
-        trim_to_occupied_bricks(p.vol, s, d, ar.amin, ar.amax - ar.amin, p.n_points, kb, ke);
-      }
+      if (p.vol.bbox) trim_sample_range(p.vol, s, d, ar.amin, ar.amax - ar.amin, p.n_points, kb, ke);
       mine = (unsigned long long)(ke - kb);
     }
   }

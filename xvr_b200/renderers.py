@@ -34,7 +34,8 @@ class _VolumeTexture:
     """Block-linear (layered cudaArray) copy of the volume behind a texture object, re-uploaded whenever the
     source tensor is a different object or has been modified in place (torch's version counter)."""
 
-    def __init__(self):
+    def __init__(self, texture=True):
+        self.texture = texture  # False: occupancy only (xvr_occupancy_create) -- what the Siddon entries take
         self.handle = None
         self.shape = None
         self.device = None
@@ -43,14 +44,14 @@ class _VolumeTexture:
 
     def get(self, volume):
         mode = os.environ.get("XVR_B200_GATHER", "tex")
-        if mode == "ldg":
+        if mode == "ldg" and self.texture:
             return None
         shape = tuple(volume.shape)
         if self.handle is None or shape != self.shape or volume.device != self.device:
             self.free()
             h = ctypes.c_void_p()
             with torch.cuda.device(volume.device):
-                call("xvr_volume_create", *shape, ctypes.byref(h))
+                call("xvr_volume_create" if self.texture else "xvr_occupancy_create", *shape, ctypes.byref(h))
             self.handle, self.shape, self.device, self.src = h, shape, volume.device, None
         if self.src is None or self.src() is not volume or self.version != volume._version:
             call("xvr_volume_upload", self.handle, ptr(volume), stream())
@@ -63,7 +64,7 @@ class _VolumeTexture:
         self.src = None
 
     def __deepcopy__(self, memo):
-        return _VolumeTexture()  # device resources are per-instance: the copy re-creates its own lazily
+        return _VolumeTexture(self.texture)  # device resources are per-instance: the copy re-creates its own lazily
 
     def free(self):
         if self.handle is not None:
@@ -208,6 +209,7 @@ class _RenderDRR(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, volume, cam2vox, cam2world, det9, det_hw, kind, args, voltex):
+        # voltex: the volume's texture handle (trilinear) / occupancy handle (siddon), or None
         cam2vox, cam2world = cuda_f32(cam2vox, "cam2vox"), cuda_f32(cam2world, "cam2world")
         B = cam2vox.shape[0]
         H, W = det_hw
@@ -221,7 +223,7 @@ class _RenderDRR(torch.autograd.Function):
             return out
         staged = os.environ.get("XVR_B200_STAGED", "0")
         if kind == "siddon":
-            call("xvr_siddon_drr_fwd", ptr(volume), *volume.shape, ptr(cam2vox), ptr(cam2world), det, B, H, W, *args,
+            call("xvr_siddon_drr_fwd", ptr(volume), voltex, *volume.shape, ptr(cam2vox), ptr(cam2world), det, B, H, W, *args,
                  lw, cw, ptr(out), ptr(jac), _lib.opts_word(), stream())
         elif staged == "1" and volume.shape[2] % 4 == 0 and volume.data_ptr() % 16 == 0:
             # bricks staged in shared memory by the TMA unit (csrc/trilinear_staged.cu)
@@ -323,6 +325,7 @@ class Siddon(torch.nn.Module):
         self.eps = eps
         self.detector_hw = None
         self._labels = _LabelCache()
+        self._texture = _VolumeTexture(texture=False)  # occupancy only: the traversal gathers from the linear volume
 
     def dims(self, volume):
         return torch.tensor(volume.shape).to(volume) + 1
@@ -338,4 +341,4 @@ class Siddon(torch.nn.Module):
         origin, row_step, col_step = detector.pixel_basis()
         return _RenderDRR.apply(volume, cam2vox, cam2world, (*origin, *row_step, *col_step),
                                 (detector.height, detector.width), "siddon",
-                                (float(self.voxel_shift), float(self.eps)), None)
+                                (float(self.voxel_shift), float(self.eps)), self._texture.get(volume))
