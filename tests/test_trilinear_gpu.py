@@ -257,15 +257,20 @@ def test_volume_gradient_matches_oracle_and_is_deterministic(cuda, n, h, b, volg
 
 
 def test_texture_and_linear_gathers_agree_bitwise(cuda, monkeypatch):
-    """The TLD4 path fetches the same fp32 texels as the scalar-load path: images and gradients are identical."""
+    """The TLD4 path fetches the same fp32 texels as the scalar-load path: images and gradients are identical.  (One lane
+    per ray: with several, the lanes slice the TRIMMED sample range, which only the texture handle knows -- same sums,
+    grouped differently.)"""
+    from xvr_b200._lib import options
+
     drr = make_drr(64, 32)
     rot, xyz = pose_params(3, seed=9)
     res = []
     for mode in ("tex", "ldg"):
         monkeypatch.setenv("XVR_B200_GATHER", mode)
         r, x = rot.clone().requires_grad_(), xyz.clone().requires_grad_()
-        img = _render(drr, r, x)
-        img.sum().backward()
+        with options(ksplit=0):
+            img = _render(drr, r, x)
+            img.sum().backward()
         res.append((img.detach(), r.grad, x.grad))
     for other in res[1:]:
         for a, b in zip(res[0], other):

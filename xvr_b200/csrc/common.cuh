@@ -128,13 +128,51 @@ __device__ __forceinline__ AlphaRange alpha_range(const float s[3], const float 
   return r;
 }
 
+// 3-D DDA through the occupancy grid along s + t d from t0 towards t1: the t at which the ray enters the first occupied
+// brick (t0 if it starts in one), +inf if there is none.
+__device__ __forceinline__ float first_occupied_brick(const Vol& v, const float s[3], const float d[3], float t0,
+                                                      float t1) {
+  const float inv = 1.0f / (float)OCC_BRICK;
+  const int nb[3] = {v.nb0, v.nb1, v.nb2};
+  int c[3], stp[3];
+  float tmax[3], tdel[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const float pos = fmaf(t0, d[a], s[a]);
+    c[a] = (int)floorf(pos * inv);
+    stp[a] = d[a] > 0.f ? 1 : -1;
+    if (d[a] != 0.f) {
+      tdel[a] = fabsf((float)OCC_BRICK / d[a]);
+      tmax[a] = ((float)((c[a] + (d[a] > 0.f ? 1 : 0)) * OCC_BRICK) - s[a]) / d[a];
+    } else {
+      tdel[a] = INFINITY;
+      tmax[a] = INFINITY;
+    }
+  }
+  float t_cur = t0;
+  const int max_steps = nb[0] + nb[1] + nb[2] + 4;
+  for (int it = 0; it < max_steps; ++it) {
+    const int b0 = min(max(c[0], 0), nb[0] - 1), b1 = min(max(c[1], 0), nb[1] - 1), b2 = min(max(c[2], 0), nb[2] - 1);
+    if (__ldg(v.occ + ((int64_t)b0 * nb[1] + b1) * nb[2] + b2)) return t_cur;
+    const float t_exit = fminf(fminf(tmax[0], tmax[1]), tmax[2]);
+    if (!(t_exit < t1)) break;
+    if (tmax[0] <= tmax[1] && tmax[0] <= tmax[2]) { c[0] += stp[0]; tmax[0] += tdel[0]; }
+    else if (tmax[1] <= tmax[2]) { c[1] += stp[1]; tmax[1] += tdel[1]; }
+    else { c[2] += stp[2]; tmax[2] += tdel[2]; }
+    t_cur = t_exit;
+  }
+  return INFINITY;
+}
+
 // Where along the ray s + alpha d can a NON-ZERO voxel be touched?  Narrows [first, last] (in: the alpha range of
 // interest, out: from the entry into the first occupied region to the exit from the last one); false if nowhere.
 //   stage 1 -- the box of the volume's non-zero voxels, widened to (lo - 2, hi + 2): a trilinear sample at x reads the
 //     voxels floor(x), floor(x) + 1, a Siddon midpoint resolves to a voxel within one of floor(x); the second voxel is
 //     for rays that run along a face of the box within rounding (slab test on one side, positions on the other);
 //   stage 2 -- a 3-D DDA through the occupancy grid of OCC_BRICK^3 bricks (a brick is occupied if, grown by two voxels,
-//     it holds a non-zero voxel: same two reasons).  Empty bricks BETWEEN occupied ones are not cut out.
+//     it holds a non-zero voxel: same two reasons), walked in from BOTH ends up to the first occupied brick each way:
+//     a ray through a body surrounded by air visits the air bricks only (one that meets nothing occupied walks its
+//     whole length once and is dropped).  Empty bricks BETWEEN occupied ones are not cut out.
 // Everything outside [first, last] contributes exact zeros to a line integral and to its derivatives; callers add their
 // own margin along the ray for the rounding of the alphas.
 __device__ __forceinline__ bool occupied_alpha_range(const Vol& v, const float s[3], const float d[3], float& first,
@@ -157,41 +195,14 @@ __device__ __forceinline__ bool occupied_alpha_range(const Vol& v, const float s
     last = tout;
     return true;
   }
-  const float inv = 1.0f / (float)OCC_BRICK;
-  const int nb[3] = {v.nb0, v.nb1, v.nb2};
-  int c[3], stp[3];
-  float tmax[3], tdel[3];
-#pragma unroll
-  for (int a = 0; a < 3; ++a) {
-    const float pos = fmaf(tin, d[a], s[a]);
-    c[a] = (int)floorf(pos * inv);
-    stp[a] = d[a] > 0.f ? 1 : -1;
-    if (d[a] != 0.f) {
-      tdel[a] = fabsf((float)OCC_BRICK / d[a]);
-      tmax[a] = ((float)((c[a] + (d[a] > 0.f ? 1 : 0)) * OCC_BRICK) - s[a]) / d[a];
-    } else {
-      tdel[a] = INFINITY;
-      tmax[a] = INFINITY;
-    }
-  }
-  float t_cur = tin, f = INFINITY, l = -INFINITY;
-  const int max_steps = nb[0] + nb[1] + nb[2] + 4;
-  for (int it = 0; it < max_steps; ++it) {
-    const int b0 = min(max(c[0], 0), nb[0] - 1), b1 = min(max(c[1], 0), nb[1] - 1), b2 = min(max(c[2], 0), nb[2] - 1);
-    const float t_exit = fminf(fminf(tmax[0], tmax[1]), tmax[2]);
-    if (__ldg(v.occ + ((int64_t)b0 * nb[1] + b1) * nb[2] + b2)) {
-      f = fminf(f, t_cur);
-      l = fminf(t_exit, tout);
-    }
-    if (!(t_exit < tout)) break;
-    if (tmax[0] <= tmax[1] && tmax[0] <= tmax[2]) { c[0] += stp[0]; tmax[0] += tdel[0]; }
-    else if (tmax[1] <= tmax[2]) { c[1] += stp[1]; tmax[1] += tdel[1]; }
-    else { c[2] += stp[2]; tmax[2] += tdel[2]; }
-    t_cur = t_exit;
-  }
-  if (!(f <= l)) return false;
-  first = f;
-  last = l;
+  const float f = first_occupied_brick(v, s, d, tin, tout);
+  if (f == INFINITY) return false;
+  const float nd[3] = {-d[0], -d[1], -d[2]};
+  const float lb = first_occupied_brick(v, s, nd, -tout, -tin);
+  // the brick found above is on the way back too, unless the reversed walk rounds a grazed face the other way
+  const float l = lb == INFINITY ? tout : -lb;
+  first = fminf(f, l);
+  last = fmaxf(f, l);
   return true;
 }
 

@@ -125,10 +125,16 @@ __global__ void __launch_bounds__(256, XVR_TRI_MIN_CTAS) trilinear_fwd_kernel(co
   float sumV = 0.f;
   float A[3] = {0.f, 0.f, 0.f}, U[3] = {0.f, 0.f, 0.f};
 
-  // this lane's slice of the samples (all of them unless several lanes share the ray)
+  // The samples this ray marches (empty-space trimming), then this lane's slice of them (all of them unless several
+  // lanes share the ray).  The slices divide the TRIMMED range: every lane of a ray gets the same share of real work.
   const int part = (tid & 31) >> (5 - ks);
-  int kbeg = (int)(((int64_t)np * part) >> ks), kend = (int)(((int64_t)np * (part + 1)) >> ks);
+  int kbeg = 0, kend = np;
   if (p.vol.bbox) trim_sample_range(p.vol, s, d, ar.amin, span, np, kbeg, kend);
+  if (ks > 0) {  // n_points < 2^26 (checked by the host): the products fit 32 bits
+    const int len = kend - kbeg;
+    kend = kbeg + ((len * (part + 1)) >> ks);
+    kbeg = kbeg + ((len * part) >> ks);
+  }
 
   if (live && !misses_padded_box(s, d, p.vol)) {
     const float lstep = 1.0f / (float)(np - 1);
@@ -469,7 +475,7 @@ static int fill_common(TrilinearParams& p, const float* volume, const void* volt
                        int n_points, int step_mode, float eps, int det_h, int det_w, int lane_w_log2,
                        int cta_w_log2, int opts, bool allow_ksplit = true) {
   if (!volume || ((!source || !target || !raylen) && !p.fused) || B <= 0 || N <= 0 || D0 < 2 || D1 < 2 || D2 < 2 ||
-      n_points < 2 || step_mode < 0 || step_mode > 2 || C < 1 || (labels && C > 255) || (!labels && C != 1) ||
+      n_points < 2 || n_points >= (1 << 26) || step_mode < 0 || step_mode > 2 || C < 1 || (labels && C > 255) || (!labels && C != 1) ||
       (opts & ~XVR_OPT_KNOWN) || (opts & XVR_OPT_KSPLIT_MASK) > 4) {
     set_last_error("xvr_trilinear: invalid argument");
     return XVR_ERR_INVALID;

@@ -19,15 +19,17 @@ from ._lib import call, cuda_f32, ptr, stream
 __all__ = ["Trilinear", "Siddon"]
 
 
-def _tile_shape():
-    """(lane_w_log2, cta_w_log2): each warp takes a 32-row x 1-column strip of detector pixels and a CTA eight
-    adjacent strips (detector rows run along the volume's contiguous axis in the usual AP/PA set-up), unless
-    overridden for tuning."""
+def _tile_shape(kind="trilinear"):
+    """(lane_w_log2, cta_w_log2), unless overridden for tuning.  Trilinear: each warp takes a 32-row x 1-column strip of
+    detector pixels and a CTA eight adjacent strips (detector rows run along the volume's contiguous axis in the usual
+    AP/PA set-up: the TLD4 footprints of neighbouring lanes overlap).  Siddon: compact 4-row x 8-column warps, eight
+    stacked in a CTA -- its scattered one-voxel gathers care less about the axis than about rays of similar length
+    sharing a warp (measured on config 5: 33.9 vs 35.7 ms at B = 64, scripts/sweep_tiles.py)."""
     env = os.environ.get("XVR_B200_TILE")
     if env:
         lw, cw = (int(v) for v in env.split(","))
         return lw, cw
-    return 0, 3
+    return (3, 3) if kind == "siddon" else (0, 3)
 
 
 class _VolumeTexture:
@@ -144,7 +146,7 @@ class _RenderRays(torch.autograd.Function):
     def forward(ctx, volume, source, target, raylen, labels, C, kind, args, det_hw, voltex):
         source, target, raylen = cuda_f32(source, "source"), cuda_f32(target, "target"), cuda_f32(raylen, "raylen")
         B, N = _check_rays(volume, source, target, raylen)
-        lw, cw = _tile_shape()
+        lw, cw = _tile_shape(kind)
         det_h, det_w = det_hw if det_hw is not None and det_hw[0] * det_hw[1] == N else (0, 0)
         need_pose_grad = any(ctx.needs_input_grad[1:4])
         need_vol_grad = ctx.needs_input_grad[0]
@@ -213,7 +215,7 @@ class _RenderDRR(torch.autograd.Function):
         cam2vox, cam2world = cuda_f32(cam2vox, "cam2vox"), cuda_f32(cam2world, "cam2world")
         B = cam2vox.shape[0]
         H, W = det_hw
-        lw, cw = _tile_shape()
+        lw, cw = _tile_shape(kind)
         out = torch.empty(B, 1, H * W, device=volume.device, dtype=torch.float32)
         jac = torch.empty(B, 7, H * W, device=volume.device, dtype=torch.float32) if ctx.needs_input_grad[1] else None
         det = (ctypes.c_float * 9)(*det9)
