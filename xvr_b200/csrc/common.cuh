@@ -34,7 +34,10 @@ struct Vol {
   int nb0, nb1, nb2;                // voxels holds a non-zero voxel
 };
 
-constexpr int OCC_BRICK = 16;
+#ifndef XVR_OCC_BRICK
+#define XVR_OCC_BRICK 16
+#endif
+constexpr int OCC_BRICK = XVR_OCC_BRICK;
 
 // Opaque handle behind xvr_volume_* (include/xvr_b200.h): a block-linear layered array + point-sampled texture.
 // The array has D0 + 2 layers: volume layer x lives in array layer x + 1, array layers 0 and D0 + 1 are zero, so
