@@ -368,8 +368,9 @@ def test_channel_collapsed_gradient_uses_the_saved_jacobian(cuda, renderer):
 
 
 # ------------------------------------------------------------------------------------------ empty-space trimming
+@pytest.mark.parametrize("ksplit", [0, 2], ids=["1lane", "4lanes"])
 @pytest.mark.parametrize("scene", ["phantom", "blob", "dense", "zeros", "labels", "edge"])
-def test_empty_space_trimming_is_bit_identical(cuda, scene):
+def test_empty_space_trimming_is_bit_identical(cuda, scene, ksplit):
     """The forward kernels skip samples outside the box of the volume's non-zero voxels (exact zeros for every sum):
     images, label channels and pose gradients equal the full march bit for bit -- air margins, a small blob in a sea of
     zeros, a volume without a single zero, an all-zero volume, label channels, rays missing / grazing / starting inside."""
@@ -392,7 +393,9 @@ def test_empty_space_trimming_is_bit_identical(cuda, scene):
         rot, xyz = torch.tensor(EDGE_ROT, device=cuda), torch.tensor(EDGE_XYZ, device=cuda)
     outs = []
     for trim in (True, False):
-        with options(trim=trim, ksplit=0):
+        # several lanes per ray: lane p adds up the samples k = p (mod lanes) -- absolute residue classes, the same
+        # samples in the same order whatever the trimming cut away
+        with options(trim=trim, ksplit=ksplit):
             r, x = rot.clone().requires_grad_(), xyz.clone().requires_grad_()
             img = drr(xvr_b200.convert(r, x, parameterization="euler_angles", convention="ZXY"),
                       mask_to_channels=scene == "labels")

@@ -125,16 +125,16 @@ __global__ void __launch_bounds__(256, XVR_TRI_MIN_CTAS) trilinear_fwd_kernel(co
   float sumV = 0.f;
   float A[3] = {0.f, 0.f, 0.f}, U[3] = {0.f, 0.f, 0.f};
 
-  // The samples this ray marches (empty-space trimming), then this lane's slice of them (all of them unless several
-  // lanes share the ray).  The slices divide the TRIMMED range: every lane of a ray gets the same share of real work.
+  // The samples this ray marches (empty-space trimming), then this lane's share of them (all of them unless several
+  // lanes share the ray): the samples k = part (mod lanes per ray).  Interleaved, not contiguous slices: the lanes of a
+  // ray then sample neighbouring positions in the same iteration (their TLD4 footprints share cache lines), every lane
+  // gets the same share of the TRIMMED range, and -- the residue classes being absolute -- each lane adds up the same
+  // samples in the same order whatever the trimming cut away (bit-identical with and without it).
   const int part = (tid & 31) >> (5 - ks);
+  const int stride = 1 << ks;
   int kbeg = 0, kend = np;
   if (p.vol.bbox) trim_sample_range(p.vol, s, d, ar.amin, span, np, kbeg, kend);
-  if (ks > 0) {  // n_points < 2^26 (checked by the host): the products fit 32 bits
-    const int len = kend - kbeg;
-    kend = kbeg + ((len * (part + 1)) >> ks);
-    kbeg = kbeg + ((len * part) >> ks);
-  }
+  kbeg += (part - kbeg) & (stride - 1);
 
   if (live && !misses_padded_box(s, d, p.vol)) {
     const float lstep = 1.0f / (float)(np - 1);
@@ -164,12 +164,13 @@ __global__ void __launch_bounds__(256, XVR_TRI_MIN_CTAS) trilinear_fwd_kernel(co
     const int half = np / 2;
     int k = kbeg;
     const int k1 = min(kend, half);
+    const float fstride = (float)stride;
     float kf = (float)k;
     XVR_UNROLL(XVR_TRI_UNROLL)
-    for (; k < k1; ++k, kf += 1.0f) sample(lstep * kf);
+    for (; k < k1; k += stride, kf += fstride) sample(lstep * kf);
     float rf = (float)(np - 1 - k);
     XVR_UNROLL(XVR_TRI_UNROLL)
-    for (; k < kend; ++k, rf -= 1.0f) sample(linspace_tail(lstep, rf));
+    for (; k < kend; k += stride, rf -= fstride) sample(linspace_tail(lstep, rf));
   }
 
   if (ks > 0) {  // combine the slices (fixed order: deterministic); slice 0 writes
