@@ -71,23 +71,68 @@ __global__ void __launch_bounds__(256) volume_bbox_kernel(const float* __restric
     atomicMin(bbox + 2, s_zlo); atomicMax(bbox + 5, s_zhi);
   }
 }
-// Occupancy of OCC_BRICK^3 bricks: 1 if the brick GROWN BY TWO VOXELS on every side holds a non-zero voxel -- a sample
+// ---- Occupancy distance field for the marchers' empty-space trimming (occupied_alpha_range, common.cuh).
+// A brick of OCC_BRICK^3 voxels is OCCUPIED if, GROWN BY TWO VOXELS on every side, it holds a non-zero voxel: a sample
 // whose cell floor(x) lies in an unoccupied brick reads 8 zero corners (floor(x) + 1 is inside the brick grown by one),
-// with one more voxel for rays that graze a brick face within rounding (trim_to_occupied_bricks, csrc/trilinear.cu).
-__global__ void __launch_bounds__(256) volume_occupancy_kernel(const float* __restrict__ vol, int D0, int D1, int D2,
-                                                               int nb1, int nb2, uint8_t* __restrict__ occ) {
-  const int b = blockIdx.x;
-  const int bx = b / (nb1 * nb2), by = (b / nb2) % nb1, bz = b % nb2;
-  constexpr int G = OCC_BRICK + 4;
-  const int x0 = bx * OCC_BRICK - 2, y0 = by * OCC_BRICK - 2, z0 = bz * OCC_BRICK - 2;
-  int any = 0;
-  for (int i = threadIdx.x; i < G * G * G && !any; i += 256) {
-    const int x = x0 + i / (G * G), y = y0 + (i / G) % G, z = z0 + i % G;
-    if ((unsigned)x < (unsigned)D0 && (unsigned)y < (unsigned)D1 && (unsigned)z < (unsigned)D2)
-      any = vol[((int64_t)x * D1 + y) * D2 + z] != 0.f;
+// with one more voxel for rays that graze a brick face within rounding.  What the kernels read is, per brick, the
+// CHEBYSHEV DISTANCE (in bricks, capped at OCC_DIST_CAP) to the nearest occupied brick, 0 for an occupied one: a ray in
+// a brick at distance D can advance (D - 1) bricks along its fastest axis without meeting an occupied brick.
+// Three steps per upload, each voxel read once:
+//   1. flags of 2^3-voxel cells (any non-zero voxel): one warp per row of cells, coalesced float2 loads;
+//   2. brick occupancy = OR of the cell flags over the brick and one ring of cells around it (= grown by two voxels);
+//   3. the distance transform, separable for the max-norm: D(c) = min_dx max(|dx|, min_dy max(|dy|, min_dz:occ |dz|)).
+__global__ void __launch_bounds__(256) volume_cell_flags_kernel(const float* __restrict__ vol, int D0, int D1, int D2,
+                                                                int m1, int m2, uint8_t* __restrict__ cells) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;  // row of cells: (x2, y2)
+  const int x2 = row / m1, y2 = row - x2 * m1;
+  if (x2 * 2 >= D0) return;
+  for (int z2 = lane; z2 < m2; z2 += 32) {
+    int any = 0;
+#pragma unroll
+    for (int dx = 0; dx < 2; ++dx)
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy) {
+        const int x = 2 * x2 + dx, y = 2 * y2 + dy;
+        if (x < D0 && y < D1) {
+          const float* r = vol + ((int64_t)x * D1 + y) * D2 + 2 * z2;
+          any |= r[0] != 0.f;
+          if (2 * z2 + 1 < D2) any |= r[1] != 0.f;
+        }
+      }
+    cells[((int64_t)x2 * m1 + y2) * m2 + z2] = (uint8_t)any;
   }
-  any = __syncthreads_or(any);
-  if (threadIdx.x == 0) occ[b] = any ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(256) volume_brick_occupancy_kernel(const uint8_t* __restrict__ cells, int m0, int m1,
+                                                                     int m2, int nb0, int nb1, int nb2,
+                                                                     uint8_t* __restrict__ dist) {
+  const int b = blockIdx.x * 256 + threadIdx.x;
+  if (b >= nb0 * nb1 * nb2) return;
+  const int bx = b / (nb1 * nb2), by = (b / nb2) % nb1, bz = b % nb2;
+  constexpr int H = OCC_BRICK / 2;  // cells per brick edge
+  int any = 0;
+  for (int x = max(bx * H - 1, 0); x < min((bx + 1) * H + 1, m0) && !any; ++x)
+    for (int y = max(by * H - 1, 0); y < min((by + 1) * H + 1, m1) && !any; ++y)
+      for (int z = max(bz * H - 1, 0); z < min((bz + 1) * H + 1, m2); ++z) any |= cells[((int64_t)x * m1 + y) * m2 + z];
+  dist[b] = any ? 0 : OCC_DIST_CAP;
+}
+
+// one separable pass along `axis` (0, 1, 2): out(c) = min over |o| <= OCC_DIST_CAP of max(|o|, in(c + o e_axis))
+__global__ void __launch_bounds__(256) occupancy_distance_pass_kernel(const uint8_t* __restrict__ in,
+                                                                      uint8_t* __restrict__ out, int nb0, int nb1,
+                                                                      int nb2, int axis) {
+  const int b = blockIdx.x * 256 + threadIdx.x;
+  if (b >= nb0 * nb1 * nb2) return;
+  const int c[3] = {b / (nb1 * nb2), (b / nb2) % nb1, b % nb2};
+  const int n = axis == 0 ? nb0 : (axis == 1 ? nb1 : nb2);
+  const int stride = axis == 0 ? nb1 * nb2 : (axis == 1 ? nb2 : 1);
+  const int i = c[axis];
+  int best = in[b];
+  for (int o = 1; o < best; ++o) {  // a neighbour |o| away cannot improve on best <= |o|
+    if (i - o >= 0) best = min(best, max(o, (int)in[b - o * stride]));
+    if (i + o < n) best = min(best, max(o, (int)in[b + o * stride]));
+  }
+  out[b] = (uint8_t)best;
 }
 }  // namespace xvr
 
@@ -111,6 +156,8 @@ static int volume_create(int D0, int D1, int D2, void** out, bool with_texture) 
   vt->D2 = D2;
   vt->bbox = nullptr;
   vt->occ = nullptr;
+  vt->occ_tmp = nullptr;
+  vt->cells = nullptr;
   vt->nb0 = (D0 + xvr::OCC_BRICK - 1) / xvr::OCC_BRICK;
   vt->nb1 = (D1 + xvr::OCC_BRICK - 1) / xvr::OCC_BRICK;
   vt->nb2 = (D2 + xvr::OCC_BRICK - 1) / xvr::OCC_BRICK;
@@ -153,13 +200,18 @@ static int volume_create(int D0, int D1, int D2, void** out, bool with_texture) 
       const int whole[6] = {0, 0, 0, D0 - 1, D1 - 1, D2 - 1};
       e = cudaMemcpy(vt->bbox, whole, sizeof(whole), cudaMemcpyHostToDevice);
     }
-    if (e == cudaSuccess) e = cudaMalloc(&vt->occ, (size_t)vt->nb0 * vt->nb1 * vt->nb2);
-    if (e == cudaSuccess) e = cudaMemset(vt->occ, 1, (size_t)vt->nb0 * vt->nb1 * vt->nb2);  // until the first upload
+    const size_t nbricks = (size_t)vt->nb0 * vt->nb1 * vt->nb2;
+    if (e == cudaSuccess) e = cudaMalloc(&vt->occ, nbricks);
+    if (e == cudaSuccess) e = cudaMemset(vt->occ, 0, nbricks);  // until the first upload: every brick occupied
+    if (e == cudaSuccess) e = cudaMalloc(&vt->occ_tmp, nbricks);
+    if (e == cudaSuccess) e = cudaMalloc(&vt->cells, (size_t)((D0 + 1) / 2) * ((D1 + 1) / 2) * ((D2 + 1) / 2));
     if (e != cudaSuccess) {
       if (vt->tex) cudaDestroyTextureObject(vt->tex);
       if (vt->array) cudaFreeArray(vt->array);
       if (vt->bbox) cudaFree(vt->bbox);
       if (vt->occ) cudaFree(vt->occ);
+      if (vt->occ_tmp) cudaFree(vt->occ_tmp);
+      if (vt->cells) cudaFree(vt->cells);
     }
   }
   if (e != cudaSuccess) {
@@ -201,8 +253,18 @@ extern "C" int xvr_volume_upload(void* handle, const float* volume, void* stream
   xvr::volume_bbox_kernel<<<dim3((vt->D1 + 7) / 8, vt->D0), 256, 0, (cudaStream_t)stream>>>(volume, vt->D1, vt->D2, vt->bbox);
   int rc = xvr::check_launch("xvr_volume_upload/bbox");
   if (rc) return rc;
-  xvr::volume_occupancy_kernel<<<vt->nb0 * vt->nb1 * vt->nb2, 256, 0, (cudaStream_t)stream>>>(
-      volume, vt->D0, vt->D1, vt->D2, vt->nb1, vt->nb2, vt->occ);
+  {
+    cudaStream_t st = (cudaStream_t)stream;
+    const int m0 = (vt->D0 + 1) / 2, m1 = (vt->D1 + 1) / 2, m2 = (vt->D2 + 1) / 2;
+    const int nbricks = vt->nb0 * vt->nb1 * vt->nb2, grid = (nbricks + 255) / 256;
+    xvr::volume_cell_flags_kernel<<<(m0 * m1 + 7) / 8, 256, 0, st>>>(volume, vt->D0, vt->D1, vt->D2, m1, m2, vt->cells);
+    xvr::volume_brick_occupancy_kernel<<<grid, 256, 0, st>>>(vt->cells, m0, m1, m2, vt->nb0, vt->nb1, vt->nb2, vt->occ);
+    // three passes, ping-pong: occ -> tmp -> occ -> tmp, and the result back into occ (the pointer the kernels hold)
+    xvr::occupancy_distance_pass_kernel<<<grid, 256, 0, st>>>(vt->occ, vt->occ_tmp, vt->nb0, vt->nb1, vt->nb2, 2);
+    xvr::occupancy_distance_pass_kernel<<<grid, 256, 0, st>>>(vt->occ_tmp, vt->occ, vt->nb0, vt->nb1, vt->nb2, 1);
+    xvr::occupancy_distance_pass_kernel<<<grid, 256, 0, st>>>(vt->occ, vt->occ_tmp, vt->nb0, vt->nb1, vt->nb2, 0);
+    cudaMemcpyAsync(vt->occ, vt->occ_tmp, (size_t)nbricks, cudaMemcpyDeviceToDevice, st);
+  }
   return xvr::check_launch("xvr_volume_upload/occupancy");
 }
 
@@ -230,6 +292,8 @@ extern "C" int xvr_volume_destroy(void* handle) {
   if (vt->array) cudaFreeArray(vt->array);
   if (vt->bbox) cudaFree(vt->bbox);
   if (vt->occ) cudaFree(vt->occ);
+  if (vt->occ_tmp) cudaFree(vt->occ_tmp);
+  if (vt->cells) cudaFree(vt->cells);
   delete vt;
   return XVR_OK;
 }

@@ -30,14 +30,15 @@ struct Vol {
   int s0, s1;  // element strides of axis 0 / 1 (D1*D2, D2)
   cudaTextureObject_t tex;  // optional layered-2D copy: layer = axis 0, height = axis 1, width = axis 2
   const int* __restrict__ bbox;  // optional DEVICE int[6]: first / last index of a non-zero voxel per axis (lo0 lo1 lo2 hi0 hi1 hi2)
-  const uint8_t* __restrict__ occ;  // optional occupancy of OCC_BRICK^3 bricks, (nb0,nb1,nb2): 1 if the brick grown by two
-  int nb0, nb1, nb2;                // voxels holds a non-zero voxel
+  const uint8_t* __restrict__ occ;  // optional (nb0,nb1,nb2) distance field over OCC_BRICK^3 bricks: Chebyshev distance in
+  int nb0, nb1, nb2;                // bricks to the nearest OCCUPIED one (grown by two voxels, it holds a non-zero voxel)
 };
 
 #ifndef XVR_OCC_BRICK
-#define XVR_OCC_BRICK 16
+#define XVR_OCC_BRICK 8
 #endif
-constexpr int OCC_BRICK = XVR_OCC_BRICK;
+constexpr int OCC_BRICK = XVR_OCC_BRICK;  // even (the occupancy is built from flags of 2^3-voxel cells)
+constexpr int OCC_DIST_CAP = 24;          // largest distance the field stores (bricks)
 
 // Opaque handle behind xvr_volume_* (include/xvr_b200.h): a block-linear layered array + point-sampled texture.
 // The array has D0 + 2 layers: volume layer x lives in array layer x + 1, array layers 0 and D0 + 1 are zero, so
@@ -47,8 +48,10 @@ struct VolumeTexture {
   cudaTextureObject_t tex;
   int D0, D1, D2;
   int* bbox;  // DEVICE int[6], refreshed by every upload: the box of the volume's non-zero voxels (empty: lo = D, hi = -1)
-  uint8_t* occ;  // DEVICE (nb0,nb1,nb2) brick occupancy, refreshed by every upload
+  uint8_t* occ;  // DEVICE (nb0,nb1,nb2) brick distance field (0 = occupied), refreshed by every upload
   int nb0, nb1, nb2;
+  uint8_t* occ_tmp;  // scratch of the distance transform, same size
+  uint8_t* cells;    // scratch: any-non-zero flags of 2^3-voxel cells
 };
 
 // The 2x2 (axis1, axis2) footprint around texel-corner (u, v) of one layer in a single TEX instruction.
@@ -131,40 +134,49 @@ __device__ __forceinline__ AlphaRange alpha_range(const float s[3], const float 
   return r;
 }
 
-// 3-D DDA through the occupancy grid along s + t d from t0 towards t1: the t at which the ray enters the first occupied
-// brick (t0 if it starts in one), +inf if there is none.
+// Walk through the brick distance field along s + t d from t0 towards t1: (a lower bound within one probe offset of) the
+// t at which the ray enters the first occupied brick, t0 if it starts in one, +inf if there is none.
+// In a brick at Chebyshev distance D >= 1 from the nearest occupied brick the ray may advance (D - 1) bricks along its
+// fastest axis -- every brick it can reach is free -- and in any case to the exit of the brick it is in; the next brick
+// is then probed a hundredth of a brick further on (a brick cut by less than that is covered by the two voxels its
+// neighbours' occupancy is grown by).  A handful of steps through a wide margin of air, one per brick next to the body.
+// If the step budget runs out the walk reports the point it reached: conservative (less is trimmed), never wrong.
 __device__ __forceinline__ float first_occupied_brick(const Vol& v, const float s[3], const float d[3], float t0,
                                                       float t1) {
-  const float inv = 1.0f / (float)OCC_BRICK;
+  constexpr float BK = (float)OCC_BRICK, INV = 1.0f / (float)OCC_BRICK;
   const int nb[3] = {v.nb0, v.nb1, v.nb2};
-  int c[3], stp[3];
-  float tmax[3], tdel[3];
+  float invd[3], off[3], up[3];
+  float dmax = 0.f;
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
-    const float pos = fmaf(t0, d[a], s[a]);
-    c[a] = (int)floorf(pos * inv);
-    stp[a] = d[a] > 0.f ? 1 : -1;
-    if (d[a] != 0.f) {
-      tdel[a] = fabsf((float)OCC_BRICK / d[a]);
-      tmax[a] = ((float)((c[a] + (d[a] > 0.f ? 1 : 0)) * OCC_BRICK) - s[a]) / d[a];
-    } else {
-      tdel[a] = INFINITY;
-      tmax[a] = INFINITY;
+    const bool moving = d[a] != 0.f;
+    invd[a] = moving ? 1.0f / d[a] : 0.f;
+    off[a] = moving ? 0.f : INFINITY;  // an axis the ray does not move along never ends a brick
+    up[a] = d[a] > 0.f ? 1.f : 0.f;
+    dmax = fmaxf(dmax, fabsf(d[a]));
+  }
+  if (!(dmax > 0.f)) return t0;
+  const float jump = BK / dmax, probe = 0.01f * jump;
+  float t = t0, entered = t0;
+  for (int it = 0; it < 4 * OCC_DIST_CAP + 64; ++it) {
+    float cf[3];
+    int c[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      cf[a] = floorf(fmaf(t, d[a], s[a]) * INV);
+      c[a] = min(max((int)cf[a], 0), nb[a] - 1);
     }
+    const int D = __ldg(v.occ + ((int64_t)c[0] * nb[1] + c[1]) * nb[2] + c[2]);
+    if (D == 0) return entered;
+    float t_exit = INFINITY;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) t_exit = fminf(t_exit, fmaf((cf[a] + up[a]) * BK - s[a], invd[a], off[a]));
+    entered = fmaxf(t_exit, t);  // (a position outside the grid is looked up in the nearest brick: keep moving on)
+    t = fmaxf(entered + probe, fmaf((float)(D - 1), jump, t));
+    if (!(entered < t1)) return INFINITY;
+    if (t > t1) t = t1;  // the last stretch ends in the brick of t1: probe that one too
   }
-  float t_cur = t0;
-  const int max_steps = nb[0] + nb[1] + nb[2] + 4;
-  for (int it = 0; it < max_steps; ++it) {
-    const int b0 = min(max(c[0], 0), nb[0] - 1), b1 = min(max(c[1], 0), nb[1] - 1), b2 = min(max(c[2], 0), nb[2] - 1);
-    if (__ldg(v.occ + ((int64_t)b0 * nb[1] + b1) * nb[2] + b2)) return t_cur;
-    const float t_exit = fminf(fminf(tmax[0], tmax[1]), tmax[2]);
-    if (!(t_exit < t1)) break;
-    if (tmax[0] <= tmax[1] && tmax[0] <= tmax[2]) { c[0] += stp[0]; tmax[0] += tdel[0]; }
-    else if (tmax[1] <= tmax[2]) { c[1] += stp[1]; tmax[1] += tdel[1]; }
-    else { c[2] += stp[2]; tmax[2] += tdel[2]; }
-    t_cur = t_exit;
-  }
-  return INFINITY;
+  return entered;
 }
 
 // Where along the ray s + alpha d can a NON-ZERO voxel be touched?  Narrows [first, last] (in: the alpha range of
