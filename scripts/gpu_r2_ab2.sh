@@ -1,3 +1,3 @@
 #!/bin/bash
-V=$PWD/build_probe/v
-for v in "$@"; do XVR_B200_LIB=$V/$v.so python scripts/sweep_tiles.py siddon:64 3,3 2>&1 | tail -1; done
+timeout 300 python -m pytest tests/test_siddon_gpu.py tests/test_golden_gpu.py tests/test_volume_gradient_gpu.py -x -q -m gpu 2>&1 | tail -1
+python scripts/sweep_tiles.py siddon:64 3,3 2>&1 | tail -1
