@@ -42,15 +42,20 @@ long long xvr_launch_count(void);
  * the trilinear kernels prefer.  Optional: pass NULL as `voltex` below to gather from the linear volume. */
 int xvr_volume_create(int D0, int D1, int D2, void** handle_out);
 /* the same handle without the texture copy (no D0 <= 2046 limit, no second copy of the volume): only the non-zero box
- * and the brick occupancy that xvr_volume_upload records -- what the Siddon entries take as `occupancy` */
+ * and the brick distance field that xvr_volume_upload records -- what the Siddon entries take as `occupancy` */
 int xvr_occupancy_create(int D0, int D1, int D2, void** handle_out);
 int xvr_volume_upload(void* handle, const float* volume, void* stream);
 int xvr_volume_destroy(void* handle);
-/* Every upload also records the box of the volume's NON-ZERO voxels (transform_hu_to_density maps air to exactly 0, and CT
- * volumes carry wide margins of it): the trilinear forward kernels skip the samples whose 8 corners all lie outside it
- * -- exact zeros for every running sum, so images and Jacobians are bit-identical to the full march
- * (XVR_OPT_NO_TRIM switches it off).  bbox6: HOST int[6] = lo0 lo1 lo2 hi0 hi1 hi2 (lo = D, hi = -1 for an all-zero
- * volume); synchronises `stream`. */
+/* Empty-space trimming.  transform_hu_to_density (trainer.py:196-197) maps air to exactly 0 and CT volumes carry wide
+ * margins of it.  Every upload therefore also records, on `stream` and graph-capturably, (i) the box of the volume's
+ * NON-ZERO voxels and (ii) a distance field over 8^3-voxel bricks: per brick the Chebyshev distance, in bricks, to the
+ * nearest brick that -- grown by two voxels -- holds a non-zero voxel.  The forward kernels that are given the handle
+ * (xvr_trilinear_*_fwd via `voltex`, xvr_siddon_drr_fwd / xvr_siddon_trace via `occupancy`) sphere-trace that field in
+ * from both ends of every ray and march only between the entry into the first occupied brick and the exit from the last
+ * one.  What is left out are samples with 8 zero corners / segments in zero voxels: exact zeros for every running sum,
+ * so images and Jacobians are bit-identical to the full march.  XVR_OPT_NO_TRIM switches it off per call.
+ * xvr_volume_bbox: bbox6 = HOST int[6] = lo0 lo1 lo2 hi0 hi1 hi2 (lo = D, hi = -1 for an all-zero volume);
+ * synchronises `stream`. */
 int xvr_volume_bbox(void* handle, int* bbox6, void* stream);
 /* samples xvr_trilinear_drr_fwd marches for a batch (counter: zeroed DEVICE unsigned long long) -- bench.py's executed
  * share under the trimming */
