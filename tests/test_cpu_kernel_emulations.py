@@ -1,7 +1,7 @@
-"""CPU transliterations of kernel logic that could not be run on a GPU when it was written:
+"""CPU transliterations of kernel logic (several were written before the kernel had run on a GPU):
 each script replays a kernel's control flow / index arithmetic thread by thread and compares it with a brute force or
 with the oracle's bit-exact reconstruction.  They are evidence about the *algorithms*; the CUDA sources are gated by
-the GPU tests in tests/test_zzz_unrun_gpu.py."""
+the GPU tests (tests/test_*_gpu.py)."""
 
 import os
 import re
@@ -35,3 +35,13 @@ def test_gather_kernel_window_logic_is_exact_with_the_source_inside_the_volume()
     out = _run("emulate_gather_kernel.py", "3")
     m = re.search(r"sum \|err\| ([0-9.]+) bad voxels (\d+)", out)
     assert m and float(m.group(1)) < 1e-6 and int(m.group(2)) == 0
+
+
+def test_empty_space_trimming_never_drops_a_sample_that_touches_density():
+    """The brick distance field (cell flags -> grown bricks -> separable Chebyshev transform, checked against its
+    definition) and the two-ended sphere-tracing walk, emulated in fp32 over 18 000 random rays (sources far, near and
+    inside; axis-parallel and plane-grazing rays) through random sparse volumes with odd shapes: every sample with a
+    non-zero corner lies inside the trimmed range."""
+    out = _run("emulate_trim_walk.py")
+    m = re.search(r"rays (\d+) missed samples (\d+)", out)
+    assert m and int(m.group(1)) >= 18_000 and int(m.group(2)) == 0
