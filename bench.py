@@ -65,6 +65,16 @@ def profiled_traffic(kernel, batch):
         return None, None
 
 
+def profiled_limiter(kernel):
+    """What the committed ncu --set full capture of `kernel` says bounds it (unit utilisations of that launch, per cent
+    of peak) -- context for `roofline`, NOT measured in this run; None without a capture."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f)[kernel].get("limiter")
+    except Exception:
+        return None
+
+
 def host_threads():
     """All the host threads this process may use (torchrun exports OMP_NUM_THREADS=1: undo that for the CPU arm)."""
     try:
@@ -332,10 +342,10 @@ def run_config(name, steps, warmup, rank, world, device, with_clocks=True):
             dist.all_reduce(t_off, op=dist.ReduceOp.MAX)
         unit = "samples" if name == "trilinear" else "segments"
         what = ("samples whose 8 corners lie outside the box of the volume's non-zero voxels / before the first and "
-                "after the last occupied 16^3 brick on the ray are skipped (exact zeros for every sum: images and "
+                "after the last occupied 8^3 brick on the ray (brick distance field, sphere-traced from both ends) are skipped (exact zeros for every sum: images and "
                 "Jacobians bit-identical to the full march, "
                 "tests/test_trilinear_gpu.py::test_empty_space_trimming_is_bit_identical)" if name == "trilinear" else
-                "plane crossings before a ray enters the first occupied 16^3 brick and after it leaves the last one are "
+                "plane crossings before a ray enters the first occupied 8^3 brick and after it leaves the last one are "
                 "dropped (the segments are air: exact zeros for the line integral and the Jacobian sums, images and "
                 "Jacobians bit-identical to the full traversal, "
                 "tests/test_siddon_gpu.py::test_empty_space_trimming_is_bit_identical, "
@@ -460,7 +470,8 @@ def run_config(name, steps, warmup, rank, world, device, with_clocks=True):
         "roofline": {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "entry_point": entry, "traffic": traffic,
                      "traffic_source": traffic_src, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg,
-                     "algorithmic_bytes": alg_note, "kernel_ms": k_avg},
+                     "algorithmic_bytes": alg_note, "kernel_ms": k_avg,
+                     "limiter_from_profile": profiled_limiter(entry)},
         "roofline_step": {"note": "SURVEY 8(d) fwd+bwd(pose) figure (two gather passes) over the whole step time",
                           "achieved": two_pass * alg * steps / (ms * 1e-3) / 1e9,
                           "frac": two_pass * alg * steps / (ms * 1e-3) / 1e9 / peak},

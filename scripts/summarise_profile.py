@@ -45,6 +45,9 @@ def raw_page(rep):
     return [dict(zip(hdr, zip(units, r))) for r in rows[2:]]
 
 
+limiter = {}
+
+
 def summarise_full(rep, name):
     recs = raw_page(rep)
     lines = [f"# ncu --set full --clock-control none: {os.path.basename(rep)} ({tag})", ""]
@@ -61,6 +64,13 @@ def summarise_full(rep, name):
             return float(v.replace(",", "")) * scale
         t = gb("dram__bytes_read.sum") + gb("dram__bytes_write.sum")
         traffic[kname] = t
+        pct = lambda key: round(float(rec[key][1].replace(",", "")), 1) if key in rec else None  # noqa: E731
+        limiter[kname] = {
+            "tex_writeback_active_pct": pct("l1tex__tex_writeback_active.avg.pct_of_peak_sustained_elapsed"),
+            "issue_active_pct": pct("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+            "dram_throughput_pct": pct("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
+            "lanes_active_of_32": pct("smsp__thread_inst_executed_per_inst_executed.ratio"),
+            "l1_hit_pct": pct("l1tex__t_sector_hit_rate.pct"), "l2_hit_pct": pct("lts__t_sector_hit_rate.pct")}
         lines += ["", f"DRAM traffic (read + write) for this launch: {t / 1e9:.3f} GB", ""]
     open(os.path.join(out, f"{tag}_{name}_ncu_full.md"), "w").write("\n".join(lines))
     return traffic
@@ -94,7 +104,8 @@ for rep, name, entry, batch in ((f"{tag}_prof_trilinear_fwd.ncu-rep", "trilinear
                                 (f"{tag}_prof_staged.ncu-rep", "trilinear_staged", "xvr_trilinear_drr_fwd_staged", 116)):
     if os.path.exists(os.path.join(g, rep)):
         t = summarise_full(os.path.join(g, rep), name)
-        tr[entry] = {"dram_bytes_per_launch": max(t.values()), "batch": batch,
+        top = max(t, key=t.get)
+        tr[entry] = {"dram_bytes_per_launch": t[top], "batch": batch, "limiter": limiter.get(top),
                      "source": f"profiles/{tag}_{name}_ncu_full.md (ncu --set full capture, not the timed run)"}
 for rep, name in ((f"{tag}_prof_volgrad.ncu-rep", "volume_grad_brick"), (f"{tag}_prof_siddon_volgrad.ncu-rep", "siddon_volume_grad")):
     if os.path.exists(os.path.join(g, rep)):
