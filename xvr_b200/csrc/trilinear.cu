@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(256, XVR_TRI_MIN_CTAS) trilinear_fwd_kernel(co
     const float fstride = (float)stride;
     float kf = (float)k;
 #if XVR_TRI_PIPE > 0
-    if (TEX && !LABELS) {
+    if (TEX) {
       // Software pipeline, XVR_TRI_PIPE samples deep.  The march waits on texture LATENCY (long-scoreboard 73 % of the
       // stall samples, the tex queue never full, the pipe 73 % busy), and under the 80-register cap of 3 CTAs per SM the
       // compiler's schedule of the plain unrolled loop keeps only 4 TLD4 per lane in flight.  Here a ring of PIPE slots
@@ -180,23 +180,26 @@ __global__ void __launch_bounds__(256, XVR_TRI_MIN_CTAS) trilinear_fwd_kernel(co
       // to the plain loop.  Measured at config 2 (ms per step): plain 7.11, PIPE 3 / 4 / 5 / 6 = 6.89 / 6.74 / 6.76 /
       // 6.83 (from 5 on the slots spill inside the loop).
       constexpr int PIPE = XVR_TRI_PIPE;
-      struct Slot { float4 a, b; };
+      struct Slot { float4 a, b; int ch; };  // ch: label channel of the sample (LABELS only; fetched with the corners)
       auto issue = [&](float u, Slot& q) {
         const float alpha = fmaf(u, span, ar.amin);
-        const float fx0 = floorf(fmaf(alpha, d[0], s[0])), fy0 = floorf(fmaf(alpha, d[1], s[1]));
-        const float fz0 = floorf(fmaf(alpha, d[2], s[2]));
+        const float x = fmaf(alpha, d[0], s[0]), y = fmaf(alpha, d[1], s[1]), z = fmaf(alpha, d[2], s[2]);
+        const float fx0 = floorf(x), fy0 = floorf(y), fz0 = floorf(z);
         const float tu = fz0 + 1.0f, tv = fy0 + 1.0f;
         const unsigned last = (unsigned)(p.vol.D0 + 1);
         const int ix = (int)fx0;
         q.a = gather_yz(p.vol.tex, (int)min((unsigned)(ix + 1), last), tu, tv);
         q.b = gather_yz(p.vol.tex, (int)min((unsigned)(ix + 2), last), tu, tv);
+        if (LABELS) q.ch = sample_label(p.labels, p.vol, x, y, z);
       };
       auto consume = [&](float u, const Slot& q) {
         const float alpha = fmaf(u, span, ar.amin);
         const float x = fmaf(alpha, d[0], s[0]), y = fmaf(alpha, d[1], s[1]), z = fmaf(alpha, d[2], s[2]);
         const float fx = x - floorf(x), fy = y - floorf(y), fz = z - floorf(z);
         float g[3];
-        sumV += trilinear_interp<JAC>(q.a.w, q.a.z, q.a.x, q.a.y, q.b.w, q.b.z, q.b.x, q.b.y, fx, fy, fz, g);
+        const float v = trilinear_interp<JAC>(q.a.w, q.a.z, q.a.x, q.a.y, q.b.w, q.b.z, q.b.x, q.b.y, fx, fy, fz, g);
+        if (LABELS) chan_acc[q.ch * 256 + tid] += v;
+        else sumV += v;
         if (JAC) {
 #pragma unroll
           for (int a = 0; a < 3; ++a) {
