@@ -29,6 +29,12 @@ extern "C" {
 #define XVR_OPT_VOLGRAD_GATHER 0x20       /* dL/dvolume: voxel-centric gather (cross-check) instead of the brick-local scatter */
 #define XVR_OPT_NO_TRIM 0x40              /* trilinear forward: march all n_points samples, also those outside the box of
                                            * the volume's non-zero voxels (the default skips them: exact zeros) */
+#define XVR_OPT_LABEL_BRICKS 0x80         /* trilinear forward with label channels: the `labels` buffer continues, at the next
+                                           * multiple of 256 bytes after its D0*D1*D2 label bytes, with a (ceil(D0/8),
+                                           * ceil(D1/8),ceil(D2/8)) uint8 table: the label every voxel of that 8^3 brick
+                                           * grown by one voxel carries (outside the volume = 0), or 255 if they differ.
+                                           * Uniform bricks answer the nearest-label lookup from the table (L1-resident)
+                                           * instead of the volume-sized array; same channels to the bit. */
 #define XVR_OPT_SIDDON_TOL(code) ((code) << 8) /* test hook: tolerance of the fast voxel-index certificate; 0 production,
                                            * 1 always the reference's exact arithmetic, 2/3/4 = x 1/2, 1/4, 1/8 (margin probes) */
 
@@ -96,6 +102,14 @@ int xvr_trilinear_drr_fwd(const float* volume, const void* voltex, int D0, int D
                           const float* cam2world, const float* det9, int B, int det_h, int det_w, int n_points,
                           int step_mode, float eps, int lane_w_log2, int cta_w_log2, float* out, float* jac,
                           int opts, void* stream);
+/* the same with label channels = DRR.forward(..., mask_to_channels=True) / trainer.py:283-289 with mask=seg, rays
+ * generated in the kernel: out (B,C,H*W); jac (B,7,H*W) or NULL = the Jacobian of the channel SUM (what a caller that
+ * collapses the channels differentiates, trainer.py:294; backward = xvr_drr_jac_bwd on the summed upstream gradient).
+ * labels / C / XVR_OPT_LABEL_BRICKS as in xvr_trilinear_rays_fwd. */
+int xvr_trilinear_drr_fwd_labels(const float* volume, const void* voltex, int D0, int D1, int D2, const uint8_t* labels,
+                                 int C, const float* cam2vox, const float* cam2world, const float* det9, int B,
+                                 int det_h, int det_w, int n_points, int step_mode, float eps, int lane_w_log2,
+                                 int cta_w_log2, float* out, float* jac, int opts, void* stream);
 /* gG (B,3,4) = dL/d cam2vox from the saved Jacobian and gout (B,1,H*W).  workspace: NULL, or
  * 12 * B * xvr_drr_jac_bwd_slices(B, H*W) floats so that small batches spread each pose over several CTAs */
 int xvr_drr_jac_bwd_slices(int B, int N);

@@ -521,3 +521,34 @@ def test_options_word_encoding():
     with pytest.raises(ValueError), options(ksplit=7):
         pass
     assert opts_word() == 0
+
+
+def test_label_brick_table_matches_brute_force():
+    """renderers._labels_with_brick_table: label bytes first, then (256-byte aligned) the per-brick table of
+    XVR_OPT_LABEL_BRICKS -- the label shared by every voxel of the 8^3 brick grown by one voxel (outside = 0), else 255."""
+    from xvr_b200.renderers import LABEL_BRICK, _labels_with_brick_table
+
+    g = torch.Generator().manual_seed(5)
+    uniform = mixed = 0
+    for shape in [(40, 32, 48), (19, 8, 27), (7, 33, 10)]:
+        lab = torch.zeros(shape, dtype=torch.uint8)
+        lab[2:, 1:, 3:] = 1  # a body that reaches three faces of the volume
+        lab[5:9, 2:6, 4:20] = 3
+        lab[tuple(int(torch.randint(0, n, (1,), generator=g)) for n in shape)] = 254
+        view = _labels_with_brick_table(lab.float())
+        n = lab.numel()
+        assert torch.equal(view, lab) and view.dtype == torch.uint8
+        buf = torch.empty(0, dtype=torch.uint8).set_(view.untyped_storage())
+        nb = [(d + LABEL_BRICK - 1) // LABEL_BRICK for d in shape]
+        table = buf[(n + 255) // 256 * 256:].view(nb)
+        padded = torch.zeros([b * LABEL_BRICK + 2 for b in nb], dtype=torch.uint8)
+        padded[1:shape[0] + 1, 1:shape[1] + 1, 1:shape[2] + 1] = lab
+        for b0 in range(nb[0]):
+            for b1 in range(nb[1]):
+                for b2 in range(nb[2]):
+                    blk = padded[b0 * 8:b0 * 8 + 10, b1 * 8:b1 * 8 + 10, b2 * 8:b2 * 8 + 10]
+                    want = int(blk.flatten()[0]) if bool((blk == blk.flatten()[0]).all()) else 255
+                    assert int(table[b0, b1, b2]) == want, (shape, b0, b1, b2)
+        uniform += int((table != 255).sum())
+        mixed += int((table == 255).sum())
+    assert uniform > 0 and mixed > 0

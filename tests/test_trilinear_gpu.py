@@ -340,12 +340,16 @@ def test_errors_are_loud(cuda):
         drr.renderer(drr.density, source, target, torch.ones(1, 1, 3, device=cuda))
 
 
-@pytest.mark.parametrize("renderer", ["trilinear", "siddon"])
-def test_channel_collapsed_gradient_uses_the_saved_jacobian(cuda, renderer):
+@pytest.mark.parametrize("renderer,fused", [("trilinear", "0"), ("trilinear", "1"), ("siddon", "1")])
+def test_channel_collapsed_gradient_uses_the_saved_jacobian(cuda, monkeypatch, renderer, fused):
     """trainer.py:292-294 collapses the label channels right after rendering (img.sum(dim=1)); autograd then hands
     the renderer one shared upstream gradient (stride 0 along the channels) and the backward is the Jacobian
     epilogue.  It must equal the per-channel recompute backward fed the same (materialised) gradient, and the
-    gradient of the unlabelled render."""
+    gradient of the unlabelled render.  On the ray entry points (XVR_B200_FUSED=0, and Siddon's label channels always)
+    both backwards see the same rays: 1e-4.  The fused trilinear label render generates its rays in the kernel and
+    hands a per-channel gradient to the ray entry point's recompute backward: different rounding of the ray end points
+    -> the noisy-phantom gradient bar there."""
+    monkeypatch.setenv("XVR_B200_FUSED", fused)
     drr = make_drr(64, 32, renderer=renderer, with_labels=True)
     rot, xyz = pose_params(3, seed=6)
     w = torch.rand(3, 1, 32, 32, generator=torch.Generator().manual_seed(1)).to(cuda)
@@ -361,7 +365,7 @@ def test_channel_collapsed_gradient_uses_the_saved_jacobian(cuda, renderer):
             img = img.sum(dim=1, keepdim=True) if mode == "collapsed" else (img * torch.ones_like(img)).sum(1, keepdim=True)
         (img * w).sum().backward()
         grads.append(torch.cat([r.grad, x.grad], 1))
-    assert rel_l2(grads[0], grads[1]) < 1e-4
+    assert rel_l2(grads[0], grads[1]) < (2e-3 if (renderer, fused) == ("trilinear", "1") else 1e-4)
     # the unlabelled render takes the fused path (rays generated in registers, not read from (B,N,3) tensors): same
     # mathematics, different rounding of the ray end points -> the noisy-phantom gradient bar
     assert rel_l2(grads[0], grads[2]) < 2e-3
@@ -414,3 +418,62 @@ def test_empty_space_trimming_is_bit_identical(cuda, scene, ksplit):
         assert list(bbox) == nz.min(0).values.tolist() + nz.max(0).values.tolist()
     if scene == "blob":
         assert outs[0][0].abs().sum() > 0
+
+
+def test_label_brick_table_gives_the_same_channels(cuda, monkeypatch):
+    """XVR_OPT_LABEL_BRICKS answers the nearest-label lookup of uniform bricks from a table: channels and pose gradients
+    equal the exact lookup bit for bit (odd volume shape, rays leaving through every face, a source inside the volume)."""
+    import numpy as np
+
+    from tests.test_zz_full_size_gpu import EDGE_ROT, EDGE_XYZ
+    from xvr_b200.data import read
+
+    g = torch.Generator().manual_seed(3)
+    hu = torch.rand(50, 45, 61, generator=g) * 1500 - 700
+    lab = torch.zeros(50, 45, 61)
+    lab[4:46, 3:40, 2:] = 1
+    lab[10:20, 8:30, 5:25] = 2
+    lab[30:33, 20:22, 40:61] = 5
+    for drr, rot, xyz in (
+            (xvr_b200.DRR(read(hu, lab, affine=np.diag([4.0, 5.0, 3.5, 1.0])), 1020.0, 40, 6.0, width=28,
+                          renderer="trilinear", reverse_x_axis=False).to(cuda), *pose_params(3, seed=31)),
+            (make_drr(64, 40, with_labels=True), torch.tensor(EDGE_ROT, device=cuda), torch.tensor(EDGE_XYZ, device=cuda))):
+        outs = []
+        for bricks in ("1", "0"):
+            monkeypatch.setenv("XVR_B200_LABEL_BRICKS", bricks)
+            r, x = rot.clone().requires_grad_(), xyz.clone().requires_grad_()
+            img = drr(xvr_b200.convert(r, x, parameterization="euler_angles", convention="ZXY"), mask_to_channels=True)
+            assert img.shape[1] > 1
+            w = torch.rand(img.shape, generator=torch.Generator().manual_seed(1)).to(cuda)
+            (img * w).sum().backward()
+            outs.append((img.detach().clone(), r.grad.clone(), x.grad.clone()))
+        for u, v in zip(*outs):
+            assert torch.equal(u, v)
+        assert outs[0][0][:, 1:].abs().sum() > 0
+
+
+def test_fused_label_channels_match_the_ray_entry_point(cuda, monkeypatch):
+    """drr(pose, mask_to_channels=True) through xvr_trilinear_drr_fwd_labels (rays generated in the kernel) against the
+    materialised-ray entry the reference's Trainer.render_samples sequence uses: channels to 1e-5 (the composed
+    camera -> voxel matrix rounds differently from the two-step transform), pose gradients to the noisy-phantom bar --
+    for the collapsed channels (the saved Jacobian of the channel sum) and for per-channel upstream gradients (the
+    fallback through the ray entry point's recompute backward)."""
+    drr = make_drr(64, 40, with_labels=True, width=28)
+    rot, xyz = pose_params(3, seed=12)
+    for collapsed in (True, False):
+        outs = []
+        for fused in ("1", "0"):
+            monkeypatch.setenv("XVR_B200_FUSED", fused)
+            r, x = rot.clone().requires_grad_(), xyz.clone().requires_grad_()
+            img = drr(xvr_b200.convert(r, x, parameterization="euler_angles", convention="ZXY"), mask_to_channels=True)
+            assert img.shape[1] > 1
+            if collapsed:
+                tot = img.sum(dim=1, keepdim=True)
+                w = torch.rand(tot.shape, generator=torch.Generator().manual_seed(2)).to(cuda)
+                (tot * w).sum().backward()
+            else:
+                w = torch.rand(img.shape, generator=torch.Generator().manual_seed(2)).to(cuda)
+                (img * w).sum().backward()
+            outs.append((img.detach().clone(), r.grad.clone(), x.grad.clone()))
+        assert rel_l2(outs[0][0], outs[1][0]) < 2e-5
+        assert rel_l2(outs[0][1], outs[1][1]) < 2e-3 and rel_l2(outs[0][2], outs[1][2]) < 2e-3

@@ -34,6 +34,9 @@ _SIGNATURES = {
     "xvr_trilinear_drr_fwd": (
         [P, P, c_int, c_int, c_int, P, P, ctypes.POINTER(c_float), c_int, c_int, c_int, c_int, c_int, c_float, c_int,
          c_int, P, P, c_int, P], c_int),
+    "xvr_trilinear_drr_fwd_labels": (
+        [P, P, c_int, c_int, c_int, P, c_int, P, P, ctypes.POINTER(c_float), c_int, c_int, c_int, c_int, c_int, c_float,
+         c_int, c_int, P, P, c_int, P], c_int),
     "xvr_trilinear_drr_fwd_staged": (
         [P, c_int, c_int, c_int, P, P, ctypes.POINTER(c_float), c_int, c_int, c_int, c_int, c_int, c_float, P, P,
          P, P], c_int),

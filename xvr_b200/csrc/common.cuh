@@ -17,7 +17,8 @@
 #define XVR_OPT_VOLGRAD_GATHER 0x20    // dL/dvolume: voxel-centric gather instead of the brick-local scatter
 #define XVR_OPT_NO_TRIM 0x40           // trilinear: march all n_points samples even outside the box of non-zero voxels
 #define XVR_OPT_SIDDON_TOL_SHIFT 8     // bits 8..11, test hook: certificate tolerance 0: x1, 1: always exact, 2..4: x1/2, 1/4, 1/8
-#define XVR_OPT_KNOWN 0xF77
+#define XVR_OPT_LABEL_BRICKS 0x80      // trilinear forward with labels: a brick table follows the label volume (see header)
+#define XVR_OPT_KNOWN 0xFF7
 
 namespace xvr {
 
@@ -339,6 +340,23 @@ __device__ __forceinline__ int sample_label(const uint8_t* __restrict__ lab, con
   if (!(rx >= 0.f && rx < (float)v.D0 && ry >= 0.f && ry < (float)v.D1 && rz >= 0.f && rz < (float)v.D2))
     return 0;
   return (int)__ldg(lab + ((int64_t)(int)rx * v.s0 + (int)ry * v.s1 + (int)rz));
+}
+
+// The same lookup through a table of OCC_BRICK^3-voxel bricks: bricks[b] = the label every voxel of brick b GROWN BY ONE
+// VOXEL carries (outside the volume counts as 0), or 255 if they differ.  A position in brick b rounds to a voxel of the
+// grown brick, so a uniform brick answers for it -- one byte from a table that stays in L1 (neighbouring lanes read the
+// same entry) instead of a scattered byte from a volume-sized array; mixed bricks (label boundaries) take the exact path.
+__device__ __forceinline__ int sample_label_bricked(const uint8_t* __restrict__ lab, const uint8_t* __restrict__ bricks,
+                                                    const Vol& v, float x, float y, float z) {
+  constexpr float INV = 1.0f / (float)OCC_BRICK;
+  const int nb0 = (v.D0 + OCC_BRICK - 1) / OCC_BRICK, nb1 = (v.D1 + OCC_BRICK - 1) / OCC_BRICK,
+            nb2 = (v.D2 + OCC_BRICK - 1) / OCC_BRICK;
+  // (NaN / far-away positions convert to a clamped brick; an edge brick is uniform only if it is all 0, the exact
+  // answer for anything outside -- and the exact path rejects them itself)
+  const int b0 = min(max((int)floorf(x * INV), 0), nb0 - 1), b1 = min(max((int)floorf(y * INV), 0), nb1 - 1),
+            b2 = min(max((int)floorf(z * INV), 0), nb2 - 1);
+  const int c = __ldg(bricks + ((int64_t)b0 * nb1 + b1) * nb2 + b2);
+  return c != 255 ? c : sample_label(lab, v, x, y, z);
 }
 
 // Thread -> detector pixel mapping.  A CTA of 256 threads covers a (256>>cta_w_log2) x (1<<cta_w_log2) pixel

@@ -24,6 +24,7 @@ namespace xvr {
 struct TrilinearParams {
   Vol vol;
   const uint8_t* __restrict__ labels;  // nullable, same shape as vol
+  const uint8_t* __restrict__ label_bricks;  // nullable: per-brick uniform label / 255 (sample_label_bricked)
   int C;                               // output channels (1 without labels)
   const float* __restrict__ source;    // (B,1,3) voxel coords
   const float* __restrict__ target;    // (B,N,3)
@@ -149,7 +150,8 @@ __global__ void __launch_bounds__(256, XVR_TRI_MIN_CTAS) trilinear_fwd_kernel(co
       float g[3];
       const float v = sample_trilinear<JAC, TEX>(p.vol, x, y, z, g);
       if (LABELS) {
-        const int c = sample_label(p.labels, p.vol, x, y, z);
+        const int c = p.label_bricks ? sample_label_bricked(p.labels, p.label_bricks, p.vol, x, y, z)
+                                     : sample_label(p.labels, p.vol, x, y, z);
         chan_acc[c * 256 + tid] += v;
       } else {
         sumV += v;
@@ -190,7 +192,9 @@ __global__ void __launch_bounds__(256, XVR_TRI_MIN_CTAS) trilinear_fwd_kernel(co
         const int ix = (int)fx0;
         q.a = gather_yz(p.vol.tex, (int)min((unsigned)(ix + 1), last), tu, tv);
         q.b = gather_yz(p.vol.tex, (int)min((unsigned)(ix + 2), last), tu, tv);
-        if (LABELS) q.ch = sample_label(p.labels, p.vol, x, y, z);
+        if (LABELS)
+          q.ch = p.label_bricks ? sample_label_bricked(p.labels, p.label_bricks, p.vol, x, y, z)
+                                : sample_label(p.labels, p.vol, x, y, z);
       };
       auto consume = [&](float u, const Slot& q) {
         const float alpha = fmaf(u, span, ar.amin);
@@ -579,6 +583,10 @@ static int fill_common(TrilinearParams& p, const float* volume, const void* volt
     }
   }
   p.labels = labels;
+  // XVR_OPT_LABEL_BRICKS: the caller's label buffer continues, at the next multiple of 256 bytes after the D0*D1*D2 label
+  // bytes, with the (nb0,nb1,nb2) brick table of sample_label_bricked (nb = ceil(D / 8))
+  p.label_bricks = (labels && (opts & XVR_OPT_LABEL_BRICKS))
+                       ? labels + (((size_t)D0 * D1 * D2 + 255) / 256) * 256 : nullptr;
   p.C = C;
   p.source = source;
   p.target = target;
@@ -756,6 +764,46 @@ extern "C" int xvr_trilinear_drr_fwd(const float* volume, const void* voltex, in
     k<<<(unsigned)grid, 256, 0, st>>>(p);
   }
   return check_launch("xvr_trilinear_drr_fwd");
+}
+
+// The fused DRR with label channels = DRR.forward(..., mask_to_channels=True) / trainer.py:283-289 with mask=seg: rays
+// generated in the kernel, out (B,C,H*W), jac (B,7,H*W) = the Jacobian of the channel SUM or NULL (what a caller that
+// collapses the channels differentiates, trainer.py:294; backward = xvr_drr_jac_bwd on the summed upstream gradient).
+// labels / C / XVR_OPT_LABEL_BRICKS as in xvr_trilinear_rays_fwd.
+extern "C" int xvr_trilinear_drr_fwd_labels(const float* volume, const void* voltex, int D0, int D1, int D2,
+                                            const uint8_t* labels, int C, const float* cam2vox,
+                                            const float* cam2world, const float* det9, int B, int det_h, int det_w,
+                                            int n_points, int step_mode, float eps, int lane_w_log2, int cta_w_log2,
+                                            float* out, float* jac, int opts, void* stream) {
+  TrilinearParams p = {};
+  p.fused = true;
+  int rc = fill_geom(p.geom, cam2vox, cam2world, det9, det_w);
+  if (rc) return rc;
+  if (!labels) {
+    set_last_error("xvr_trilinear_drr_fwd_labels: labels is null (use xvr_trilinear_drr_fwd)");
+    return XVR_ERR_INVALID;
+  }
+  rc = fill_common(p, volume, voltex, D0, D1, D2, labels, C, nullptr, nullptr, nullptr, B, det_h * det_w, n_points,
+                   step_mode, eps, det_h, det_w, lane_w_log2, cta_w_log2, opts);
+  if (rc) return rc;
+  if (!out) {
+    set_last_error("xvr_trilinear_drr_fwd_labels: out is null");
+    return XVR_ERR_INVALID;
+  }
+  p.out = out;
+  p.jac = jac;
+  const int64_t grid = (int64_t)B * p.tiles_per_pose;
+  if (grid >= (int64_t)1 << 31) {
+    set_last_error("xvr_trilinear_drr_fwd_labels: grid too large");
+    return XVR_ERR_INVALID;
+  }
+  const size_t smem = (size_t)C * 256 * sizeof(float);
+  const bool tex = p.vol.tex != 0;
+  auto k = jac ? (tex ? trilinear_fwd_kernel<true, true, true> : trilinear_fwd_kernel<true, true, false>)
+               : (tex ? trilinear_fwd_kernel<false, true, true> : trilinear_fwd_kernel<false, true, false>);
+  if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  k<<<(unsigned)grid, 256, smem, (cudaStream_t)stream>>>(p);
+  return check_launch("xvr_trilinear_drr_fwd_labels");
 }
 
 namespace xvr {

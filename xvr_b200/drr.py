@@ -197,8 +197,13 @@ class DRR(torch.nn.Module):
             raise RuntimeError("drr.density was unloaded; call drr.renderer(volume, ...) directly "
                                "(as xvr's Trainer.render_samples does) or restore it")
         mask = getattr(self, "mask", None) if mask_to_channels else None
-        fused = (mask is None and calibration is None and isinstance(self.renderer, (Trilinear, Siddon))
+        # label channels ride the fused path of the trilinear renderer (no volume gradient there: the ray entry point
+        # has the scatter for it)
+        fused_mask_ok = mask is None or (isinstance(self.renderer, Trilinear) and not self.density.requires_grad)
+        fused = (fused_mask_ok and calibration is None and isinstance(self.renderer, (Trilinear, Siddon))
                  and self.reshape and os.environ.get("XVR_B200_FUSED", "1") == "1")
+        if mask is not None and fused:
+            kwargs = dict(kwargs, mask=mask)
         degrees = kwargs.pop("degrees", False)
         if (fused and parameterization == "euler_angles" and len(args) == 2 and args[0].is_cuda and args[0].dim() == 2
                 and conv.COMPOSE_APPLIES_SELF_FIRST and os.environ.get("XVR_B200_FUSED_POSE", "1") == "1"):

@@ -115,9 +115,44 @@ class _LabelCache:
                 self.entries.pop(k)  # sources that died
             while len(self.entries) >= self.MAX_ENTRIES:
                 self.entries.pop(next(iter(self.entries)))
-            hit = (mask.to(torch.uint8).contiguous(), hi + 1, weakref.ref(mask))
+            hit = (_labels_with_brick_table(mask), hi + 1, weakref.ref(mask))
             self.entries[key] = hit
         return hit[0], hit[1]
+
+
+LABEL_BRICK = 8  # = OCC_BRICK of csrc/common.cuh
+OPT_LABEL_BRICKS = 0x80
+
+
+def _labels_with_brick_table(mask):
+    """The uint8 label volume followed -- at the next multiple of 256 bytes -- by the brick table of
+    XVR_OPT_LABEL_BRICKS (include/xvr_b200.h): per 8^3 brick the label all voxels of the brick grown by one voxel carry
+    (outside the volume = 0), 255 if they differ.  Set-up work on the label map, once per mask object (like the uint8
+    conversion itself); the trilinear forward answers the nearest-label lookup of uniform bricks from the table.
+    Returns the (D0,D1,D2) uint8 label volume as a view of the first D0*D1*D2 bytes of that buffer (what every kernel
+    reads as `labels`; `_has_brick_table` tells the two apart)."""
+    lab = mask.to(torch.uint8).contiguous()
+    n = lab.numel()
+    nb = [(d + LABEL_BRICK - 1) // LABEL_BRICK for d in lab.shape]
+    # min / max over every brick grown by one voxel: pad by 1 in front and up to the brick grid + 1 behind with 0 (= the
+    # label of everything outside), pool with window 10 / stride 8.  fp16 holds 0..255 exactly.
+    pad = []
+    for d, b in zip(reversed(lab.shape), reversed(nb)):
+        pad += [1, b * LABEL_BRICK + 1 - d]
+    x = torch.nn.functional.pad(lab.to(torch.float16)[None, None], pad)
+    hi = torch.nn.functional.max_pool3d(x, LABEL_BRICK + 2, LABEL_BRICK)
+    lo = -torch.nn.functional.max_pool3d(-x, LABEL_BRICK + 2, LABEL_BRICK)
+    table = torch.where(hi == lo, hi, torch.full_like(hi, 255.0)).to(torch.uint8).reshape(-1)
+    assert table.numel() == nb[0] * nb[1] * nb[2]
+    off = (n + 255) // 256 * 256
+    buf = torch.zeros(off + table.numel(), dtype=torch.uint8, device=lab.device)
+    buf[:n] = lab.reshape(-1)
+    buf[off:] = table
+    return buf[:n].view(lab.shape)
+
+
+def _has_brick_table(labels):
+    return labels.untyped_storage().nbytes() > labels.numel()
 
 
 def _check_rays(volume, source, target, raylen):
@@ -161,7 +196,10 @@ class _RenderRays(torch.autograd.Function):
         vol_args = (ptr(volume),) if voltex is False else (ptr(volume), voltex)
         ctx.common = (*vol_args, *volume.shape, ptr(labels), C, ptr(source), ptr(target), ptr(raylen), B, N, *args,
                       det_h, det_w, lw, cw)
-        call(f"xvr_{kind}_rays_fwd", *ctx.common, ptr(out), ptr(jac), _lib.opts_word(), stream())
+        # the label buffers of _LabelCache carry their brick table (XVR_OPT_LABEL_BRICKS; trilinear forward only)
+        bricks = (OPT_LABEL_BRICKS if labels is not None and kind == "trilinear"
+                  and _has_brick_table(labels) and os.environ.get("XVR_B200_LABEL_BRICKS", "1") != "0" else 0)
+        call(f"xvr_{kind}_rays_fwd", *ctx.common, ptr(out), ptr(jac), _lib.opts_word() | bricks, stream())
         ctx.kind, ctx.C, ctx.shape = kind, C, tuple(volume.shape)
         if need_pose_grad or need_vol_grad:
             # the recompute path (per-channel upstream gradients, d/dvolume) needs the inputs; saving them keeps the
@@ -210,20 +248,32 @@ class _RenderDRR(torch.autograd.Function):
     if the volume requires a gradient, gathers dL/dvolume voxel by voxel (no atomics, deterministic)."""
 
     @staticmethod
-    def forward(ctx, volume, cam2vox, cam2world, det9, det_hw, kind, args, voltex):
+    def forward(ctx, volume, cam2vox, cam2world, det9, det_hw, kind, args, voltex, labels=None, C=1):
         # voltex: the volume's texture handle (trilinear) / occupancy handle (siddon), or None
+        # labels / C: uint8 label volume of _LabelCache and its channel count (trilinear only) -> out (B,C,H*W)
         cam2vox, cam2world = cuda_f32(cam2vox, "cam2vox"), cuda_f32(cam2world, "cam2world")
         B = cam2vox.shape[0]
         H, W = det_hw
         lw, cw = _tile_shape(kind)
-        out = torch.empty(B, 1, H * W, device=volume.device, dtype=torch.float32)
+        out = torch.empty(B, C, H * W, device=volume.device, dtype=torch.float32)
         jac = torch.empty(B, 7, H * W, device=volume.device, dtype=torch.float32) if ctx.needs_input_grad[1] else None
         det = (ctypes.c_float * 9)(*det9)
         ctx.det = (det, B, H, W, args, tuple(volume.shape))
+        ctx.kind, ctx.labels, ctx.C, ctx.det9, ctx.volume = kind, labels, C, det9, None
         if B == 0:  # an empty pose batch renders to an empty image batch; nothing to launch
             ctx.save_for_backward(jac)
             return out
         staged = os.environ.get("XVR_B200_STAGED", "0")
+        if labels is not None:
+            if kind != "trilinear" or ctx.needs_input_grad[0]:
+                raise _lib.XvrB200Error("fused label channels: trilinear renderer, no volume gradient")
+            bricks = (OPT_LABEL_BRICKS if _has_brick_table(labels)
+                      and os.environ.get("XVR_B200_LABEL_BRICKS", "1") != "0" else 0)
+            call("xvr_trilinear_drr_fwd_labels", ptr(volume), voltex, *volume.shape, ptr(labels), C, ptr(cam2vox),
+                 ptr(cam2world), det, B, H, W, *args, lw, cw, ptr(out), ptr(jac), _lib.opts_word() | bricks, stream())
+            ctx.volume = volume  # the per-channel-gradient fallback of backward() renders again
+            ctx.save_for_backward(jac, cam2vox, cam2world)
+            return out
         if kind == "siddon":
             call("xvr_siddon_drr_fwd", ptr(volume), voltex, *volume.shape, ptr(cam2vox), ptr(cam2world), det, B, H, W, *args,
                  lw, cw, ptr(out), ptr(jac), _lib.opts_word(), stream())
@@ -243,12 +293,23 @@ class _RenderDRR(torch.autograd.Function):
     def backward(ctx, gout):
         jac, *mats = ctx.saved_tensors
         det, B, H, W, args, shape = ctx.det
+        # one upstream gradient for every channel?  (autograd hands the backward of sum(dim=1) over as a stride-0
+        # expansion: checked on the tensor as it arrives, before it is made contiguous)
+        shared = gout.shape[1] == 1 or gout.stride(1) == 0
+        if ctx.labels is not None and shared:
+            gout = gout[:, :1]
         gout = cuda_f32(gout, "grad_output")
         gG = gvol = None
         if B == 0:
             return (torch.zeros(shape, device=gout.device) if ctx.needs_input_grad[0] else None,
                     torch.zeros(0, 3, 4, device=gout.device) if ctx.needs_input_grad[1] else None,
-                    None, None, None, None, None, None)
+                    None, None, None, None, None, None, None, None)
+        if ctx.labels is not None and ctx.needs_input_grad[1]:
+            # label channels: the saved Jacobian is the one of the channel SUM -- exact whenever every channel sees the
+            # same upstream gradient (autograd hands the backward of sum(dim=1) over as a stride-0 expansion).
+            if not shared:
+                return (None, _labelled_drr_backward_by_rays(ctx, mats[0], mats[1], gout, H, W, args),
+                        None, None, None, None, None, None, None, None)
         if ctx.needs_input_grad[1]:
             gG = torch.empty(B, 3, 4, device=gout.device, dtype=torch.float32)
             slices = _lib.lib().xvr_drr_jac_bwd_slices(B, H * W)
@@ -268,7 +329,27 @@ class _RenderDRR(torch.autograd.Function):
                 work = torch.empty(B * H * W * 12, device=gout.device, dtype=torch.float32)
                 call("xvr_trilinear_drr_bwd_volume", ptr(cam2vox), ptr(vox2cam), ptr(cam2world), det, B, H, W, *args,
                      ptr(gout), *shape, ptr(work), ptr(gvol), 0, _lib.opts_word(), stream())
-        return gvol, gG, None, None, None, None, None, None
+        return gvol, gG, None, None, None, None, None, None, None, None
+
+
+def _labelled_drr_backward_by_rays(ctx, cam2vox, cam2world, gout, H, W, args):
+    """dL/dcam2vox of the fused label-channel render for an upstream gradient that differs between channels (rare: xvr
+    collapses the channels before it differentiates): the rays are materialised from the camera matrices and the
+    ray entry point's recompute backward does the work, autograd chaining it back to the matrices."""
+    o, u, v = (torch.tensor(ctx.det9[3 * i:3 * i + 3], device=gout.device, dtype=torch.float32) for i in range(3))
+    ii = torch.arange(H, device=gout.device, dtype=torch.float32).repeat_interleave(W)
+    jj = torch.arange(W, device=gout.device, dtype=torch.float32).repeat(H)
+    pts = o + ii[:, None] * u + jj[:, None] * v  # (N,3) detector points in the camera frame, row-major
+    with torch.enable_grad():
+        G = cam2vox.detach().requires_grad_()
+        source = G[:, :, 3].unsqueeze(1)
+        target = torch.einsum("bij,nj->bni", G[:, :, :3], pts) + source
+        world = torch.einsum("bij,nj->bni", cam2world[:, :, :3], pts)  # target - source in world mm
+        raylen = world.norm(dim=-1).unsqueeze(1)
+        out = _RenderRays.apply(ctx.volume, source.contiguous(), target.contiguous(), raylen.contiguous(), ctx.labels,
+                                ctx.C, "trilinear", args, (H, W), None)
+        (gG,) = torch.autograd.grad(out, G, gout)
+    return gG
 
 
 class Trilinear(torch.nn.Module):
@@ -301,15 +382,16 @@ class Trilinear(torch.nn.Module):
                                  self._texture.get(volume))
 
 
-    def render_drr(self, volume, cam2vox, cam2world, detector, n_points=conv.TRILINEAR_N_POINTS):
+    def render_drr(self, volume, cam2vox, cam2world, detector, n_points=conv.TRILINEAR_N_POINTS, mask=None):
         """Fused path used by ``DRR.forward``: ``cam2vox``/``cam2world`` are (B,3,4) camera->voxel / camera->world
-        matrices, ``detector`` supplies the pixel grid.  Returns (B,1,H*W)."""
+        matrices, ``detector`` supplies the pixel grid.  Returns (B,1,H*W), or (B,C,H*W) with a label map ``mask``."""
         volume = cuda_f32(volume, "volume")
         origin, row_step, col_step = detector.pixel_basis()
+        labels, C = (None, 1) if mask is None else self._labels.get(mask)
         return _RenderDRR.apply(volume, cam2vox, cam2world, (*origin, *row_step, *col_step),
                                 (detector.height, detector.width), "trilinear",
                                 (int(n_points), conv.STEP_MODES[self.step], float(self.eps)),
-                                self._texture.get(volume))
+                                self._texture.get(volume), labels, C)
 
 
 class Siddon(torch.nn.Module):

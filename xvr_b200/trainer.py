@@ -19,6 +19,7 @@ import torch.distributed as dist
 from .data import transform_hu_to_density
 from .metrics import DoubleGeodesicSE3, MultiscaleNormalizedCrossCorrelation2d
 from .pose import N_ANGULAR_COMPONENTS, convert
+from .renderers import Trilinear
 from .sampler import random_pose_params
 from .sharding import shard_bounds
 
@@ -198,15 +199,17 @@ class _RenderEpilogue(torch.autograd.Function):
 
 
 def render_samples_fused(drr, volume, seg, affinv, pose, img_threshold=0.10, mask_threshold=0.05):
-    """``render_samples`` through the fused kernels: without label channels the rays are generated inside the renderer
-    (no (B,N,3) tensors: 0.5 GB per batch at 256^2), and mask / channel sum / keep / per-sample min and max come out of
+    """``render_samples`` through the fused kernels: the rays are generated inside the renderer (no (B,N,3) tensors:
+    0.5 GB per batch at 256^2; label channels too, for the trilinear renderer), and mask / channel sum / keep / per-sample min and max come out of
     one epilogue launch.  Returns ``(img (B,1,H,W), mask (B,C,H,W) bool or None, keep (B,) bool, stats (B,4))``;
     ``mask`` is only formed with label channels (the Dice term is a constant without them)."""
     B = len(pose)
-    if seg is None and hasattr(drr.renderer, "render_drr"):
+    fused_labels = seg is not None and isinstance(drr.renderer, Trilinear) and not volume.requires_grad
+    if (seg is None or fused_labels) and hasattr(drr.renderer, "render_drr"):
         cam2world = drr.detector.reorient.compose(pose).matrix
         cam2vox = affinv.matrix.to(cam2world) @ cam2world
-        raw = drr.renderer.render_drr(volume, cam2vox[:, :3].contiguous(), cam2world[:, :3].contiguous(), drr.detector)
+        raw = drr.renderer.render_drr(volume, cam2vox[:, :3].contiguous(), cam2world[:, :3].contiguous(), drr.detector,
+                                      **({"mask": seg} if fused_labels else {}))
     else:
         source, target = drr.detector(pose, None)
         raylen = (target - source).norm(dim=-1).unsqueeze(1)
