@@ -147,7 +147,7 @@ int xvr_siddon_rays_fwd(const float* volume, int D0, int D1, int D2, const uint8
  * --renderer siddon): rays generated in-kernel as in xvr_trilinear_drr_fwd, out (B,1,H*W), jac (B,7,H*W) or NULL;
  * backward = xvr_drr_jac_bwd.
  * `occupancy` (NULL = none): a handle of xvr_occupancy_create (or xvr_volume_create) the volume was uploaded to.  With
- * it every ray's plane crossings are restricted to the stretch from its entry into the first occupied 16^3 brick to its
+ * it every ray's plane crossings are restricted to the stretch from its entry into the first occupied 8^3 brick to its
  * exit from the last one: the segments dropped are air (value exactly 0), i.e. exact zeros for the line integral and for
  * the Jacobian sums, so image and Jacobian are bit-identical to the full traversal (XVR_OPT_NO_TRIM switches it off). */
 int xvr_siddon_drr_fwd(const float* volume, const void* occupancy, int D0, int D1, int D2, const float* cam2vox,

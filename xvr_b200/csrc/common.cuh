@@ -185,10 +185,11 @@ __device__ __forceinline__ float first_occupied_brick(const Vol& v, const float 
 //   stage 1 -- the box of the volume's non-zero voxels, widened to (lo - 2, hi + 2): a trilinear sample at x reads the
 //     voxels floor(x), floor(x) + 1, a Siddon midpoint resolves to a voxel within one of floor(x); the second voxel is
 //     for rays that run along a face of the box within rounding (slab test on one side, positions on the other);
-//   stage 2 -- a 3-D DDA through the occupancy grid of OCC_BRICK^3 bricks (a brick is occupied if, grown by two voxels,
-//     it holds a non-zero voxel: same two reasons), walked in from BOTH ends up to the first occupied brick each way:
-//     a ray through a body surrounded by air visits the air bricks only (one that meets nothing occupied walks its
-//     whole length once and is dropped).  Empty bricks BETWEEN occupied ones are not cut out.
+//   stage 2 -- the distance field over OCC_BRICK^3 bricks (a brick is occupied if, grown by two voxels, it holds a
+//     non-zero voxel: same two reasons), sphere-traced in from BOTH ends up to the first occupied brick each way
+//     (first_occupied_brick): a ray through a body surrounded by air takes a handful of steps through the air (one
+//     that meets nothing occupied walks its whole length once and is dropped).  Empty bricks BETWEEN occupied ones are
+//     not cut out.
 // Everything outside [first, last] contributes exact zeros to a line integral and to its derivatives; callers add their
 // own margin along the ray for the rounding of the alphas.
 __device__ __forceinline__ bool occupied_alpha_range(const Vol& v, const float s[3], const float d[3], float& first,
