@@ -425,4 +425,4 @@ class Siddon(torch.nn.Module):
         origin, row_step, col_step = detector.pixel_basis()
         return _RenderDRR.apply(volume, cam2vox, cam2world, (*origin, *row_step, *col_step),
                                 (detector.height, detector.width), "siddon",
-                                (float(self.voxel_shift), float(self.eps)), self._texture.get(volume))
+                                (float(self.voxel_shift), float(self.eps)), self._texture.get(volume), None, 1)
