@@ -16,6 +16,7 @@ headline of the line instead (used for the per-config profiles under profiles/).
 
 import argparse
 import json
+import math
 import os
 import statistics
 import subprocess
@@ -411,16 +412,32 @@ def run_config(name, steps, warmup, rank, world, device, with_clocks=True):
     barrier()
     assert checksum == checksum, "e2e result is NaN"
     ms_e2e = e2.elapsed_time(e3)
+
+    # ---- sustained: the same device-resident step for >= 2 s.  The K-step region above lasts a fraction of a second --
+    # too short to show that clocks and power have settled -- so the line also carries this longer run (not the
+    # headline: `value` is exactly K steps, as the contract says); the clock sampler covers it.
+    n_sus = torch.tensor([min(3000, max(steps, math.ceil(2000.0 * steps / max(ms, 1e-3))))], device=device)
+    if world > 1:
+        dist.all_reduce(n_sus, op=dist.ReduceOp.MAX)
+    n_sus = int(n_sus.item())
+    e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e4.record()
+    for _ in range(n_sus):
+        step(rot_d, xyz_d)
+    e5.record()
+    barrier()
+    ms_sus = e4.elapsed_time(e5)
     clocks = sampler.stop() if (rank == 0 and with_clocks) else None
 
     # every rank rendered its own poses: a non-finite or all-zero image anywhere invalidates the run
     ok = torch.tensor([float(torch.isfinite(img).all() and img.abs().sum() > 0)], device=device)
-    t = torch.tensor([ms, ms_e2e], device=device, dtype=torch.float64)
+    t = torch.tensor([ms, ms_e2e, ms_sus], device=device, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
     assert ok.item() == 1.0, "a rank rendered a non-finite or empty image batch"
-    ms, ms_e2e = t.tolist()
+    ms, ms_e2e, ms_sus = t.tolist()
     if rank != 0:
         return None
 
@@ -467,6 +484,9 @@ def run_config(name, steps, warmup, rank, world, device, with_clocks=True):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "timed_seconds": ms * 1e-3,
+        "sustained": {"steps": n_sus, "seconds": ms_sus * 1e-3, "value": world * B * n_sus / (ms_sus * 1e-3),
+                      "unit": UNIT, "note": "the same device-resident step repeated for >= 2 s (clocks / power are "
+                                            "sampled over the timed, e2e and sustained regions)"},
         "roofline": {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "entry_point": entry, "traffic": traffic,
                      "traffic_source": traffic_src, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg,
