@@ -596,26 +596,18 @@ static int fill_common(TrilinearParams& p, const float* volume, const void* volt
   p.n_points = n_points;
   p.step_mode = step_mode;
   p.eps = eps;
-  // Small batches (B = 1 registration): let 2, 4 or 8 lanes share a ray.  The kernel keeps 3 CTAs per SM resident,
-  // i.e. a "wave" is 444 CTAs; pick the split whose last wave is fullest (ceil(waves) / waves smallest), preferring
-  // fewer lanes per ray on ties.  Launches of more than ~16 waves are left alone: their tail is < 6 %.
+  // Small batches (B = 1 registration): let 2, 4 or 8 lanes share a ray (interleaved samples of the trimmed range).  The
+  // kernel keeps 3 CTAs per SM resident, 444 in all: take the FEWEST lanes per ray that still give every slot a CTA.
+  // (Round 1 picked the split whose last wave was fullest; with trimmed rays a CTA's work varies from nothing to a full
+  // march, waves mean little, and every extra lane per ray costs texture locality: config 3 at 256^2, 1 / 2 / 4 / 8
+  // lanes per ray = under-filled / 0.250 / 0.252 / 0.266 ms per iteration.)
   int ks = 0;
   if (!labels && allow_ksplit) {
     if (opts & XVR_OPT_KSPLIT_MASK) {
       ks = (opts & XVR_OPT_KSPLIT_MASK) - 1;
     } else {
-      const double wave = 148.0 * XVR_TRI_MIN_CTAS;
-      double best = 1e30;
-      for (int k = 0; k <= 3; ++k) {
-        const double ctas = (double)(((int64_t)B * N << k) + 255) / 256.0;
-        const double waves = ctas / wave;
-        if (k == 0 && waves >= 16.0) break;
-        const double cost = (waves < 1.0 ? 1.0 : ceil(waves)) / waves;
-        if (cost < best - 1e-9) {
-          best = cost;
-          ks = k;
-        }
-      }
+      const int64_t slots = 148 * XVR_TRI_MIN_CTAS;
+      while (ks < 3 && ((((int64_t)B * N) << ks) + 255) / 256 < slots) ++ks;
     }
   }
   return fill_map(p.map, N, det_h, det_w, lane_w_log2, cta_w_log2, ks, &p.tiles_per_pose);
